@@ -1,0 +1,309 @@
+// Fp arithmetic for BLS12-381 on sm_100a: 381-bit Montgomery residues, R = 2^384, 12 x 32-bit limbs.
+//
+// Replaces (does not port) the reference's FP/Big/DBig layer:
+//   /root/reference/incubator-milagro-crypto-rust/src/fp.rs:306-314,390-398 (mul/sqr -> Big::mul + Big::monty)
+//   /root/reference/incubator-milagro-crypto-rust/src/big.rs:950-986,1064-1106 (7 x 58-bit limbs, R = 2^406)
+// The reference's radix and lazy-reduction bookkeeping are not observable; here every
+// value is kept fully reduced in [0, p).
+//
+// The multiplier is a row-wise Montgomery product with two 32-bit-staggered accumulators ("even"/"odd"
+// columns) so that every 32x32->64 partial product is one `mad.lo.cc`/`madc.hi.cc` pair on an aligned
+// register pair, which ptxas fuses into IMAD.WIDE(.X) carry chains.
+//
+// The same source also compiles with a plain host C++ compiler (B3_HOSTSIM) where the PTX carry-flag
+// primitives are emulated; that build exists ONLY for tests/hostsim (CPU-side debugging of the device
+// algorithms) and is never linked into the product library.
+#pragma once
+#include <stdint.h>
+
+#if defined(B3_HOSTSIM)
+#define B3_FN static inline
+#define B3_FN_NOINLINE static
+#define B3_CONST static const
+#else
+#define B3_FN __device__ __forceinline__
+#define B3_FN_NOINLINE __device__ __noinline__
+#define B3_CONST static __device__ __constant__ const
+#endif
+
+struct alignas(16) fp {
+    uint32_t l[12];
+};
+struct fp2 {
+    fp c0, c1;
+};
+
+#include "constants.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// carry-flag primitives
+// ------------------------------------------------------------------------------------------------
+#if defined(B3_HOSTSIM)
+static thread_local uint32_t b3_cc = 0;
+static inline uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; b3_cc = (uint32_t)(t >> 32); return (uint32_t)t; }
+static inline uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + b3_cc; b3_cc = (uint32_t)(t >> 32); return (uint32_t)t; }
+static inline uint32_t addc(uint32_t a, uint32_t b) { return a + b + b3_cc; }
+static inline uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b; b3_cc = (uint32_t)(t >> 63); return (uint32_t)t; }
+static inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - b3_cc; b3_cc = (uint32_t)(t >> 63); return (uint32_t)t; }
+static inline uint32_t subc(uint32_t a, uint32_t b) { return a - b - b3_cc; }
+// (lo,hi) = a*b
+static inline void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a * b; lo = (uint32_t)t; hi = (uint32_t)(t >> 32); }
+// (lo,hi) += a*b, carry chain started here
+static inline void mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    uint64_t t = (uint64_t)a * b;
+    uint64_t s = (uint64_t)lo + (uint32_t)t; lo = (uint32_t)s;
+    s = (uint64_t)hi + (uint32_t)(t >> 32) + (s >> 32); hi = (uint32_t)s; b3_cc = (uint32_t)(s >> 32);
+}
+// (lo,hi) += a*b + carry-in, carry out
+static inline void madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    uint64_t t = (uint64_t)a * b;
+    uint64_t s = (uint64_t)lo + (uint32_t)t + b3_cc; lo = (uint32_t)s;
+    s = (uint64_t)hi + (uint32_t)(t >> 32) + (s >> 32); hi = (uint32_t)s; b3_cc = (uint32_t)(s >> 32);
+}
+// (lo,hi) = a*b + (lo_in,hi_in) + carry-in, carry out
+static inline void madc_wide_cc_in(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t lo_in, uint32_t hi_in) {
+    uint64_t t = (uint64_t)a * b;
+    uint64_t s = (uint64_t)lo_in + (uint32_t)t + b3_cc; lo = (uint32_t)s;
+    s = (uint64_t)hi_in + (uint32_t)(t >> 32) + (s >> 32); hi = (uint32_t)s; b3_cc = (uint32_t)(s >> 32);
+}
+// (lo,hi) = a*b + carry-in; the high word cannot overflow; carry flag left unspecified
+static inline void madc_wide_last(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    uint64_t t = (uint64_t)a * b + b3_cc; lo = (uint32_t)t; hi = (uint32_t)(t >> 32);
+}
+#else
+B3_FN uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B3_FN uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B3_FN uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B3_FN uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B3_FN uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B3_FN uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B3_FN void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    asm volatile("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+B3_FN void mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+B3_FN void madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+B3_FN void madc_wide_cc_in(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t lo_in, uint32_t hi_in) {
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;"
+                 : "=r"(lo), "=r"(hi) : "r"(a), "r"(b), "r"(lo_in), "r"(hi_in));
+}
+B3_FN void madc_wide_last(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, 0; madc.hi.u32 %1, %2, %3, 0;" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// basic predicates / moves
+// ------------------------------------------------------------------------------------------------
+B3_FN bool fp_is_zero(const fp& a) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) t |= a.l[i];
+    return t == 0;
+}
+B3_FN bool fp_eq(const fp& a, const fp& b) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) t |= a.l[i] ^ b.l[i];
+    return t == 0;
+}
+// r = c ? a : b
+B3_FN void fp_select(fp& r, bool c, const fp& a, const fp& b) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = c ? a.l[i] : b.l[i];
+}
+B3_FN void fp_set(fp& r, const fp& a) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = a.l[i];
+}
+
+// t (in [0, 2p)) -> r in [0, p)
+B3_FN void fp_final_sub(fp& r, const uint32_t* t) {
+    uint32_t s[12];
+    s[0] = sub_cc(t[0], FP_P.l[0]);
+#pragma unroll
+    for (int i = 1; i < 12; i++) s[i] = subc_cc(t[i], FP_P.l[i]);
+    uint32_t borrow = subc(0, 0);          // 0xffffffff if t < p
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = borrow ? t[i] : s[i];
+}
+
+B3_FN void fp_add(fp& r, const fp& a, const fp& b) {
+    uint32_t t[12];
+    t[0] = add_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < 11; i++) t[i] = addc_cc(a.l[i], b.l[i]);
+    t[11] = addc(a.l[11], b.l[11]);        // a + b < 2p < 2^384: no carry out
+    fp_final_sub(r, t);
+}
+
+B3_FN void fp_sub(fp& r, const fp& a, const fp& b) {
+    uint32_t t[12];
+    t[0] = sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < 12; i++) t[i] = subc_cc(a.l[i], b.l[i]);
+    uint32_t m = subc(0, 0);               // all-ones if a < b
+    r.l[0] = add_cc(t[0], FP_P.l[0] & m);
+#pragma unroll
+    for (int i = 1; i < 11; i++) r.l[i] = addc_cc(t[i], FP_P.l[i] & m);
+    r.l[11] = addc(t[11], FP_P.l[11] & m);
+}
+
+B3_FN void fp_neg(fp& r, const fp& a) {
+    bool z = fp_is_zero(a);
+    uint32_t t[12];
+    t[0] = sub_cc(FP_P.l[0], a.l[0]);
+#pragma unroll
+    for (int i = 1; i < 11; i++) t[i] = subc_cc(FP_P.l[i], a.l[i]);
+    t[11] = subc(FP_P.l[11], a.l[11]);
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = z ? 0u : t[i];
+}
+
+B3_FN void fp_dbl(fp& r, const fp& a) { fp_add(r, a, a); }
+
+// r = a/2 mod p
+B3_FN void fp_half(fp& r, const fp& a) {
+    uint32_t m = 0u - (a.l[0] & 1u);
+    uint32_t t[12];
+    t[0] = add_cc(a.l[0], FP_P.l[0] & m);
+#pragma unroll
+    for (int i = 1; i < 11; i++) t[i] = addc_cc(a.l[i], FP_P.l[i] & m);
+    t[11] = addc(a.l[11], FP_P.l[11] & m);  // < 2p < 2^384
+#pragma unroll
+    for (int i = 0; i < 11; i++) r.l[i] = (t[i] >> 1) | (t[i + 1] << 31);
+    r.l[11] = t[11] >> 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Montgomery multiplication  r = a * b / 2^384 mod p      (a < p required; b any 384-bit value)
+// ------------------------------------------------------------------------------------------------
+// acc[0..11] = sum_{j even} x[j] * y * 2^(32 j)            (no carries: products do not overlap)
+B3_FN void b3_mul_row(uint32_t* acc, const uint32_t* x, uint32_t y) {
+#pragma unroll
+    for (int j = 0; j < 12; j += 2) mul_wide(acc[j], acc[j + 1], x[j], y);
+}
+// acc[0..11] += sum_{j even} x[j] * y * 2^(32 j); carry out left in the flag
+B3_FN void b3_mad_row(uint32_t* acc, const uint32_t* x, uint32_t y) {
+    mad_wide_cc(acc[0], acc[1], x[0], y);
+#pragma unroll
+    for (int j = 2; j < 12; j += 2) madc_wide_cc(acc[j], acc[j + 1], x[j], y);
+}
+// acc = (acc >> 64) + sum_{j even} x[j] * y * 2^(32 j) + carry-in
+B3_FN void b3_mad_row_shift(uint32_t* acc, const uint32_t* x, uint32_t y) {
+#pragma unroll
+    for (int j = 0; j < 10; j += 2) madc_wide_cc_in(acc[j], acc[j + 1], x[j], y, acc[j + 2], acc[j + 3]);
+    madc_wide_last(acc[10], acc[11], x[10], y);
+}
+// one row: (E + 2^32 O) <- ((E + 2^32 O) + a*bi + m*p) / 2^32, roles of E and O swap afterwards
+B3_FN void b3_mont_row(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t bi, bool first) {
+    if (first) {
+        b3_mul_row(odd, a + 1, bi);
+        b3_mul_row(even, a, bi);
+    } else {
+        even[0] = add_cc(even[0], odd[1]);
+        b3_mad_row_shift(odd, a + 1, bi);
+        b3_mad_row(even, a, bi);
+        odd[11] = addc(odd[11], 0);
+    }
+    uint32_t m = even[0] * FP_PINV32;
+    b3_mad_row(odd, FP_P.l + 1, m);
+    b3_mad_row(even, FP_P.l, m);
+    odd[11] = addc(odd[11], 0);
+}
+
+B3_FN void fp_mul_inl(fp& r, const fp& a, const fp& b) {
+    uint32_t even[12], odd[12], av[12], bv[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) { av[i] = a.l[i]; bv[i] = b.l[i]; }
+#pragma unroll
+    for (int i = 0; i < 12; i += 2) {
+        b3_mont_row(even, odd, av, bv[i], i == 0);
+        b3_mont_row(odd, even, av, bv[i + 1], false);
+    }
+    even[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+    for (int i = 1; i < 11; i++) even[i] = addc_cc(even[i], odd[i + 1]);
+    even[11] = addc(even[11], 0);
+    fp_final_sub(r, even);
+}
+
+B3_FN_NOINLINE void fp_mul(fp& r, const fp& a, const fp& b) { fp_mul_inl(r, a, b); }
+B3_FN_NOINLINE void fp_sqr(fp& r, const fp& a) { fp_mul_inl(r, a, a); }
+
+// Montgomery form <-> canonical
+B3_FN void fp_to_mont(fp& r, const fp& a) { fp_mul(r, FP_R2, a); }       // a any 384-bit value
+B3_FN void fp_from_mont(fp& r, const fp& a) {
+    fp one = FP_ZERO;
+    one.l[0] = 1;
+    fp_mul(r, a, one);
+}
+
+// r = a^e for a fixed public exponent e (plain 384-bit integer), 4-bit fixed window
+B3_FN_NOINLINE void fp_pow_const(fp& r, const fp& a, const fp& e) {
+    fp tbl[16];
+    tbl[0] = FP_ONE;
+    tbl[1] = a;
+    for (int i = 2; i < 16; i++) fp_mul(tbl[i], tbl[i - 1], a);
+    fp acc = FP_ONE;
+    bool started = false;
+    for (int w = 95; w >= 0; w--) {
+        uint32_t d = (e.l[w >> 3] >> ((w & 7) * 4)) & 15u;
+        if (started) {
+            fp_sqr(acc, acc); fp_sqr(acc, acc); fp_sqr(acc, acc); fp_sqr(acc, acc);
+        }
+        if (d) {
+            if (started) fp_mul(acc, acc, tbl[d]);
+            else { acc = tbl[d]; started = true; }
+        }
+    }
+    r = acc;
+}
+
+B3_FN void fp_inv(fp& r, const fp& a) { fp_pow_const(r, a, FP_EXP_INV); }   // 0 -> 0
+
+// Square root helper for p = 3 mod 4.  Given d, g = d^((p-3)/4):
+//   t = g*d, chi = t*g = d^((p-1)/2) in {0, 1, -1}.  If chi == 1: t^2 = d and 1/t = g.
+//   If chi == -1: t^2 = -d and 1/t = -g.
+// Returns is_qr (chi != -1), t and tinv = g*chi.
+B3_FN bool fp_sqrt_ratio_parts(fp& t, fp& tinv, const fp& d) {
+    fp g, chi;
+    fp_pow_const(g, d, FP_EXP_SQRT_G);
+    fp_mul(t, g, d);
+    fp_mul(chi, t, g);
+    bool is_one = fp_eq(chi, FP_ONE);
+    bool is_zero = fp_is_zero(chi);
+    fp ng;
+    fp_neg(ng, g);
+    fp_select(tinv, is_one, g, ng);
+    return is_one || is_zero;
+}
+
+// canonical integer comparison helpers (inputs canonical, NOT Montgomery)
+B3_FN bool fp_raw_gt(const fp& a, const fp& b) {      // a > b
+    uint32_t t = sub_cc(b.l[0], a.l[0]);
+#pragma unroll
+    for (int i = 1; i < 12; i++) t = subc_cc(b.l[i], a.l[i]);
+    (void)t;
+    return subc(0, 0) != 0;
+}
+B3_FN bool fp_raw_lt_p(const fp& a) { return fp_raw_gt(FP_P, a); }
+
+// 48 big-endian bytes <-> raw limbs
+B3_FN void fp_raw_from_be(fp& r, const uint8_t* b) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        const uint8_t* q = b + 44 - 4 * i;
+        r.l[i] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3];
+    }
+}
+B3_FN void fp_raw_to_be(uint8_t* b, const fp& a) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        uint8_t* q = b + 44 - 4 * i;
+        q[0] = (uint8_t)(a.l[i] >> 24); q[1] = (uint8_t)(a.l[i] >> 16); q[2] = (uint8_t)(a.l[i] >> 8); q[3] = (uint8_t)a.l[i];
+    }
+}

@@ -1,0 +1,360 @@
+// Extension tower Fp2 -> Fp6 -> Fp12 (2-3-2) for BLS12-381.
+//
+//   Fp2  = Fp[i]/(i^2+1)            Fp6 = Fp2[v]/(v^3 - xi), xi = 1+i           Fp12 = Fp6[w]/(w^2 - v)
+//
+// so an Fp12 element is sum_{k=0..5} f_k w^k with f_k in Fp2 and w^6 = xi:
+//   c0 = (w^0, w^2, w^4), c1 = (w^1, w^3, w^5).
+// The reference uses a 2-2-3 tower (/root/reference/incubator-milagro-crypto-rust/src/fp4.rs,
+// fp12.rs:300-366: Fp12 = Fp4[w]/(w^3-j), j^2 = 1+i) which holds the same six Fp2 coefficients; its wire
+// order (fp12.rs:859-913) is w^0, w^3, w^1, w^4, w^2, w^5 -- see fp12_to_wire().
+#pragma once
+#include "fp.cuh"
+
+struct fp6 {
+    fp2 c0, c1, c2;
+};
+struct fp12 {
+    fp6 c0, c1;
+};
+
+// ---------------------------------------------------------------- Fp2
+B3_FN void fp2_add(fp2& r, const fp2& a, const fp2& b) { fp_add(r.c0, a.c0, b.c0); fp_add(r.c1, a.c1, b.c1); }
+B3_FN void fp2_sub(fp2& r, const fp2& a, const fp2& b) { fp_sub(r.c0, a.c0, b.c0); fp_sub(r.c1, a.c1, b.c1); }
+B3_FN void fp2_neg(fp2& r, const fp2& a) { fp_neg(r.c0, a.c0); fp_neg(r.c1, a.c1); }
+B3_FN void fp2_dbl(fp2& r, const fp2& a) { fp_dbl(r.c0, a.c0); fp_dbl(r.c1, a.c1); }
+B3_FN void fp2_half(fp2& r, const fp2& a) { fp_half(r.c0, a.c0); fp_half(r.c1, a.c1); }
+B3_FN void fp2_conj(fp2& r, const fp2& a) { r.c0 = a.c0; fp_neg(r.c1, a.c1); }
+B3_FN bool fp2_is_zero(const fp2& a) { return fp_is_zero(a.c0) && fp_is_zero(a.c1); }
+B3_FN bool fp2_eq(const fp2& a, const fp2& b) { return fp_eq(a.c0, b.c0) && fp_eq(a.c1, b.c1); }
+B3_FN void fp2_select(fp2& r, bool c, const fp2& a, const fp2& b) { fp_select(r.c0, c, a.c0, b.c0); fp_select(r.c1, c, a.c1, b.c1); }
+B3_FN void fp2_zero(fp2& r) { r.c0 = FP_ZERO; r.c1 = FP_ZERO; }
+B3_FN void fp2_one(fp2& r) { r.c0 = FP_ONE; r.c1 = FP_ZERO; }
+
+// (a0 + a1 i)(b0 + b1 i), Karatsuba: 3 Fp mults
+B3_FN_NOINLINE void fp2_mul(fp2& r, const fp2& a, const fp2& b) {
+    fp t0, t1, s0, s1;
+    fp_add(s0, a.c0, a.c1);
+    fp_add(s1, b.c0, b.c1);
+    fp_mul(t0, a.c0, b.c0);
+    fp_mul(t1, a.c1, b.c1);
+    fp_mul(s0, s0, s1);
+    fp_sub(s0, s0, t0);
+    fp_sub(r.c1, s0, t1);
+    fp_sub(r.c0, t0, t1);
+}
+// (a0+a1)(a0-a1) + 2 a0 a1 i : 2 Fp mults
+B3_FN_NOINLINE void fp2_sqr(fp2& r, const fp2& a) {
+    fp s, d, m;
+    fp_add(s, a.c0, a.c1);
+    fp_sub(d, a.c0, a.c1);
+    fp_mul(m, a.c0, a.c1);
+    fp_mul(r.c0, s, d);
+    fp_dbl(r.c1, m);
+}
+B3_FN void fp2_mul_fp(fp2& r, const fp2& a, const fp& s) { fp_mul(r.c0, a.c0, s); fp_mul(r.c1, a.c1, s); }
+// * xi = (1+i)
+B3_FN void fp2_mul_xi(fp2& r, const fp2& a) {
+    fp t;
+    fp_sub(t, a.c0, a.c1);
+    fp_add(r.c1, a.c0, a.c1);
+    r.c0 = t;
+}
+B3_FN void fp2_mul3(fp2& r, const fp2& a) { fp2 t; fp2_dbl(t, a); fp2_add(r, t, a); }
+// 1/a = conj(a)/N(a);  0 -> 0
+B3_FN_NOINLINE void fp2_inv(fp2& r, const fp2& a) {
+    fp n, t;
+    fp_sqr(n, a.c0);
+    fp_sqr(t, a.c1);
+    fp_add(n, n, t);
+    fp_inv(n, n);
+    fp_mul(r.c0, a.c0, n);
+    fp_mul(t, a.c1, n);
+    fp_neg(r.c1, t);
+}
+// RFC 9380 sgn0 for m = 2 (= reference A/fp2.rs:449-455); input in Montgomery form
+B3_FN uint32_t fp2_sgn0(const fp2& a) {
+    fp r0, r1;
+    fp_from_mont(r0, a.c0);
+    fp_from_mont(r1, a.c1);
+    uint32_t s0 = r0.l[0] & 1u, z0 = fp_is_zero(r0) ? 1u : 0u, s1 = r1.l[0] & 1u;
+    return s0 | (z0 & s1);
+}
+
+// Square root in Fp2 with two Fp exponentiations (norm trick, p = 3 mod 4).
+//   Let n = N(a) = a0^2 + a1^2.  a is a square in Fp2 iff n is a square in Fp.
+//   If not, returns false and a root of zmul*a where N(zmul) = 5 (zmul = SSWU Z = -(2+i)) is produced
+//   from the same exponentiation: sqrt(5 n) = sqrt(-5) * sqrt(-n).
+//   root = x0 + x1 i with x0^2 = (a0 + s)/2 or x1^2 = ..., handled by the chi trick of fp_sqrt_ratio_parts.
+// out: r = sqrt(a) if a is square, else sqrt(Z * a).  Which of the two roots is unspecified.
+B3_FN_NOINLINE bool fp2_sqrt_or_z(fp2& r, const fp2& a) {
+    fp n, t, s, sinv;
+    fp_sqr(n, a.c0);
+    fp_sqr(t, a.c1);
+    fp_add(n, n, t);
+    bool sq = fp_sqrt_ratio_parts(s, sinv, n);          // s^2 = n (sq) or s^2 = -n (!sq)
+    fp2 b;
+    if (sq) {
+        b = a;
+    } else {
+        fp2_mul(b, a, SSWU_Z);                           // N(b) = 5 n, sqrt = sqrt(-5) * s
+        fp_mul(s, s, FP_SQRT_M5);
+    }
+    // now s^2 = N(b), b = b0 + b1 i.  delta = (b0 + s)/2; exactly one of delta, (b0 - s)/2 is a QR
+    // unless b1 == 0.
+    fp delta, x, xinv;
+    fp_add(delta, b.c0, s);
+    fp_half(delta, delta);
+    if (fp_is_zero(delta)) {                             // b0 = -s: then b1 = 0 and b = -|..|; use other branch
+        fp_sub(delta, b.c0, s);
+        fp_half(delta, delta);
+    }
+    bool dq = fp_sqrt_ratio_parts(x, xinv, delta);       // x^2 = +-delta, xinv = 1/x
+    // y = b1 / (2x)
+    fp y, hb1;
+    fp_half(hb1, b.c1);
+    fp_mul(y, hb1, xinv);
+    if (dq) {                                            // x^2 = delta: root = x + y i
+        r.c0 = x; r.c1 = y;
+    } else {                                             // x^2 = -delta: (y + ... ) root = y - x i ... see below
+        // (x0 + x1 i)^2 = b with x0^2 = delta_minus.  delta_minus = -b1^2/(4 delta) = (b1/(2x))^2 = y^2,
+        // so x0 = y and x1 = b1/(2 x0) = b1/(2y) = x^2 * ... = -delta*2/b1 ... use x1 = b1 * x /(2 * x^2 * y)
+        // simpler: x1 = b1/(2y) and y = b1/(2x) => x1 = x.  Check sign: (y + x i)^2 = y^2 - x^2 + 2xy i
+        //   = delta_minus + delta + b1 i = b0 + b1 i.
+        r.c0 = y; r.c1 = x;
+    }
+    return sq;
+}
+
+// ---------------------------------------------------------------- Fp6
+B3_FN void fp6_add(fp6& r, const fp6& a, const fp6& b) { fp2_add(r.c0, a.c0, b.c0); fp2_add(r.c1, a.c1, b.c1); fp2_add(r.c2, a.c2, b.c2); }
+B3_FN void fp6_sub(fp6& r, const fp6& a, const fp6& b) { fp2_sub(r.c0, a.c0, b.c0); fp2_sub(r.c1, a.c1, b.c1); fp2_sub(r.c2, a.c2, b.c2); }
+B3_FN void fp6_neg(fp6& r, const fp6& a) { fp2_neg(r.c0, a.c0); fp2_neg(r.c1, a.c1); fp2_neg(r.c2, a.c2); }
+// * v : (c0, c1, c2) -> (xi c2, c0, c1)
+B3_FN void fp6_mul_v(fp6& r, const fp6& a) {
+    fp2 t;
+    fp2_mul_xi(t, a.c2);
+    r.c2 = a.c1;
+    r.c1 = a.c0;
+    r.c0 = t;
+}
+B3_FN_NOINLINE void fp6_mul(fp6& r, const fp6& a, const fp6& b) {
+    fp2 v0, v1, v2, t0, t1, t2;
+    fp2_mul(v0, a.c0, b.c0);
+    fp2_mul(v1, a.c1, b.c1);
+    fp2_mul(v2, a.c2, b.c2);
+    // c0 = v0 + xi((a1+a2)(b1+b2) - v1 - v2)
+    fp2_add(t0, a.c1, a.c2);
+    fp2_add(t1, b.c1, b.c2);
+    fp2_mul(t0, t0, t1);
+    fp2_sub(t0, t0, v1);
+    fp2_sub(t0, t0, v2);
+    fp2_mul_xi(t0, t0);
+    fp2_add(t0, t0, v0);
+    // c1 = (a0+a1)(b0+b1) - v0 - v1 + xi v2
+    fp2_add(t1, a.c0, a.c1);
+    fp2_add(t2, b.c0, b.c1);
+    fp2_mul(t1, t1, t2);
+    fp2_sub(t1, t1, v0);
+    fp2_sub(t1, t1, v1);
+    fp2_mul_xi(t2, v2);
+    fp2_add(t1, t1, t2);
+    // c2 = (a0+a2)(b0+b2) - v0 - v2 + v1
+    fp2 u0, u1;
+    fp2_add(u0, a.c0, a.c2);
+    fp2_add(u1, b.c0, b.c2);
+    fp2_mul(u0, u0, u1);
+    fp2_sub(u0, u0, v0);
+    fp2_sub(u0, u0, v2);
+    fp2_add(r.c2, u0, v1);
+    r.c0 = t0;
+    r.c1 = t1;
+}
+B3_FN void fp6_sqr(fp6& r, const fp6& a) { fp6_mul(r, a, a); }
+// a * (b0, 0, 0)
+B3_FN void fp6_mul_fp2(fp6& r, const fp6& a, const fp2& b0) {
+    fp2_mul(r.c0, a.c0, b0); fp2_mul(r.c1, a.c1, b0); fp2_mul(r.c2, a.c2, b0);
+}
+// a * (0, b1, b2)
+B3_FN_NOINLINE void fp6_mul_by_12(fp6& r, const fp6& a, const fp2& b1, const fp2& b2) {
+    fp2 v1, v2, t0, t1, t2;
+    fp2_mul(v1, a.c1, b1);
+    fp2_mul(v2, a.c2, b2);
+    // c0 = xi (a1 b2 + a2 b1) = xi((a1+a2)(b1+b2) - v1 - v2)
+    fp2_add(t0, a.c1, a.c2);
+    fp2_add(t1, b1, b2);
+    fp2_mul(t0, t0, t1);
+    fp2_sub(t0, t0, v1);
+    fp2_sub(t0, t0, v2);
+    fp2_mul_xi(t0, t0);
+    // c1 = a0 b1 + xi v2 ; c2 = a0 b2 + v1
+    fp2_mul(t1, a.c0, b1);
+    fp2_mul_xi(t2, v2);
+    fp2_add(t1, t1, t2);
+    fp2_mul(t2, a.c0, b2);
+    fp2_add(r.c2, t2, v1);
+    r.c0 = t0;
+    r.c1 = t1;
+}
+B3_FN_NOINLINE void fp6_inv(fp6& r, const fp6& a) {
+    fp2 A, B, C, t, F;
+    fp2_sqr(A, a.c0); fp2_mul(t, a.c1, a.c2); fp2_mul_xi(t, t); fp2_sub(A, A, t);      // a0^2 - xi a1 a2
+    fp2_sqr(B, a.c2); fp2_mul_xi(B, B); fp2_mul(t, a.c0, a.c1); fp2_sub(B, B, t);      // xi a2^2 - a0 a1
+    fp2_sqr(C, a.c1); fp2_mul(t, a.c0, a.c2); fp2_sub(C, C, t);                        // a1^2 - a0 a2
+    fp2_mul(F, a.c0, A);
+    fp2_mul(t, a.c2, B); fp2_mul_xi(t, t); fp2_add(F, F, t);
+    fp2_mul(t, a.c1, C); fp2_mul_xi(t, t); fp2_add(F, F, t);
+    fp2_inv(F, F);
+    fp2_mul(r.c0, A, F); fp2_mul(r.c1, B, F); fp2_mul(r.c2, C, F);
+}
+
+// ---------------------------------------------------------------- Fp12
+B3_FN void fp12_one(fp12& r) {
+    fp2_one(r.c0.c0); fp2_zero(r.c0.c1); fp2_zero(r.c0.c2);
+    fp2_zero(r.c1.c0); fp2_zero(r.c1.c1); fp2_zero(r.c1.c2);
+}
+B3_FN bool fp12_eq(const fp12& a, const fp12& b) {
+    return fp2_eq(a.c0.c0, b.c0.c0) && fp2_eq(a.c0.c1, b.c0.c1) && fp2_eq(a.c0.c2, b.c0.c2) &&
+           fp2_eq(a.c1.c0, b.c1.c0) && fp2_eq(a.c1.c1, b.c1.c1) && fp2_eq(a.c1.c2, b.c1.c2);
+}
+B3_FN bool fp12_is_one(const fp12& a) {
+    return fp_eq(a.c0.c0.c0, FP_ONE) && fp_is_zero(a.c0.c0.c1) && fp2_is_zero(a.c0.c1) && fp2_is_zero(a.c0.c2) &&
+           fp2_is_zero(a.c1.c0) && fp2_is_zero(a.c1.c1) && fp2_is_zero(a.c1.c2);
+}
+B3_FN_NOINLINE void fp12_mul(fp12& r, const fp12& a, const fp12& b) {
+    fp6 t0, t1, s0, s1;
+    fp6_mul(t0, a.c0, b.c0);
+    fp6_mul(t1, a.c1, b.c1);
+    fp6_add(s0, a.c0, a.c1);
+    fp6_add(s1, b.c0, b.c1);
+    fp6_mul(s0, s0, s1);
+    fp6_sub(s0, s0, t0);
+    fp6_sub(r.c1, s0, t1);
+    fp6_mul_v(t1, t1);
+    fp6_add(r.c0, t0, t1);
+}
+// complex squaring: 2 Fp6 mults
+B3_FN_NOINLINE void fp12_sqr(fp12& r, const fp12& a) {
+    fp6 ab, s, t;
+    fp6_mul(ab, a.c0, a.c1);
+    fp6_add(s, a.c0, a.c1);
+    fp6_mul_v(t, a.c1);
+    fp6_add(t, t, a.c0);
+    fp6_mul(s, s, t);                      // (a0+a1)(a0+v a1) = a0^2 + v a1^2 + (1+v) a0 a1
+    fp6_sub(s, s, ab);
+    fp6_mul_v(t, ab);
+    fp6_sub(r.c0, s, t);
+    fp6_add(r.c1, ab, ab);
+}
+// conj = p^6 Frobenius: w -> -w
+B3_FN void fp12_conj(fp12& r, const fp12& a) { r.c0 = a.c0; fp6_neg(r.c1, a.c1); }
+B3_FN_NOINLINE void fp12_inv(fp12& r, const fp12& a) {
+    fp6 t0, t1;
+    fp6_sqr(t0, a.c0);
+    fp6_sqr(t1, a.c1);
+    fp6_mul_v(t1, t1);
+    fp6_sub(t0, t0, t1);
+    fp6_inv(t0, t0);
+    fp6_mul(r.c0, a.c0, t0);
+    fp6_mul(t1, a.c1, t0);
+    fp6_neg(r.c1, t1);
+}
+// multiply by a sparse line  l0 + l3 w^3 + l5 w^5  =  (l0,0,0) + (0,l3,l5) w
+B3_FN_NOINLINE void fp12_mul_by_line(fp12& f, const fp2& l0, const fp2& l3, const fp2& l5) {
+    fp6 t0, t1, s;
+    fp6_mul_fp2(t0, f.c0, l0);                       // f0 * L0
+    fp6_mul_by_12(t1, f.c1, l3, l5);                 // f1 * L1
+    fp6_add(s, f.c0, f.c1);
+    fp6 L;
+    L.c0 = l0; L.c1 = l3; L.c2 = l5;
+    fp6_mul(s, s, L);                                // (f0+f1)(L0+L1)
+    fp6_sub(s, s, t0);
+    fp6_sub(f.c1, s, t1);
+    fp6_mul_v(t1, t1);
+    fp6_add(f.c0, t0, t1);
+}
+
+// p-power Frobenius: f_k -> conj(f_k) * GAMMA1[k]
+B3_FN fp2& fp12_coef(fp12& a, int k) {
+    return (k & 1) ? ((k == 1) ? a.c1.c0 : (k == 3) ? a.c1.c1 : a.c1.c2)
+                   : ((k == 0) ? a.c0.c0 : (k == 2) ? a.c0.c1 : a.c0.c2);
+}
+B3_FN const fp2& fp12_coef(const fp12& a, int k) {
+    return (k & 1) ? ((k == 1) ? a.c1.c0 : (k == 3) ? a.c1.c1 : a.c1.c2)
+                   : ((k == 0) ? a.c0.c0 : (k == 2) ? a.c0.c1 : a.c0.c2);
+}
+B3_FN_NOINLINE void fp12_frob(fp12& r, const fp12& a) {
+    for (int k = 0; k < 6; k++) {
+        fp2 t;
+        fp2_conj(t, fp12_coef(a, k));
+        if (k == 0) fp12_coef(r, 0) = t;
+        else fp2_mul(fp12_coef(r, k), t, FROB_GAMMA1[k]);
+    }
+}
+B3_FN_NOINLINE void fp12_frob2(fp12& r, const fp12& a) {
+    fp12_coef(r, 0) = fp12_coef(a, 0);
+    for (int k = 1; k < 6; k++) fp2_mul_fp(fp12_coef(r, k), fp12_coef(a, k), FROB_GAMMA2[k]);
+}
+B3_FN_NOINLINE void fp12_frob3(fp12& r, const fp12& a) {
+    for (int k = 0; k < 6; k++) {
+        fp2 t;
+        fp2_conj(t, fp12_coef(a, k));
+        if (k == 0) fp12_coef(r, 0) = t;
+        else fp2_mul(fp12_coef(r, k), t, FROB_GAMMA3[k]);
+    }
+}
+
+// Granger-Scott squaring for elements of the cyclotomic subgroup (after the easy part of fexp).
+// Uses the Fp4 = Fp2[s]/(s^2 - xi) sub-structure with s = w^3: pairs (f0,f3), (f1,f4), (f2,f5).
+B3_FN void fp4_sqr_parts(fp2& r0, fp2& r1, const fp2& a, const fp2& b) {
+    // (a + b s)^2 = (a^2 + xi b^2) + (2ab) s
+    fp2 t0, t1, t2;
+    fp2_sqr(t0, a);
+    fp2_sqr(t1, b);
+    fp2_add(t2, a, b);
+    fp2_sqr(t2, t2);
+    fp2_sub(t2, t2, t0);
+    fp2_sub(r1, t2, t1);
+    fp2_mul_xi(t1, t1);
+    fp2_add(r0, t0, t1);
+}
+B3_FN_NOINLINE void fp12_cyclo_sqr(fp12& r, const fp12& a) {
+    // basis: a = g0 + g1 y + g2 y^2 with y = w (y^3 = s = w^3), g0 = (f0, f3), g1 = (f1, f4), g2 = (f2, f5) in Fp4.
+    // Granger-Scott: with A = g0^2, B = g2^2 * s, C = g1^2 :
+    //   r.g0 = 3A - 2 conj(g0);  r.g1 = 3B + 2 conj(g1);  r.g2 = 3C - 2 conj(g2)     (conj: s -> -s)
+    fp2 A0, A1, B0, B1, C0, C1, t;
+    const fp2 &f0 = fp12_coef(a, 0), &f1 = fp12_coef(a, 1), &f2 = fp12_coef(a, 2),
+              &f3 = fp12_coef(a, 3), &f4 = fp12_coef(a, 4), &f5 = fp12_coef(a, 5);
+    fp4_sqr_parts(A0, A1, f0, f3);
+    fp4_sqr_parts(C0, C1, f1, f4);
+    fp4_sqr_parts(B0, B1, f2, f5);
+    // B * s : (b0 + b1 s) s = xi b1 + b0 s
+    fp2_mul_xi(t, B1);
+    B1 = B0;
+    B0 = t;
+    fp2 o0, o1, o2, o3, o4, o5;
+    // g0' = 3A - 2 conj(g0) = (3A0 - 2 f0) + (3A1 + 2 f3) s
+    fp2_sub(t, A0, f0); fp2_dbl(t, t); fp2_add(o0, t, A0);
+    fp2_add(t, A1, f3); fp2_dbl(t, t); fp2_add(o3, t, A1);
+    // g1' = 3B + 2 conj(g1) = (3B0 + 2 f1) + (3B1 - 2 f4) s
+    fp2_add(t, B0, f1); fp2_dbl(t, t); fp2_add(o1, t, B0);
+    fp2_sub(t, B1, f4); fp2_dbl(t, t); fp2_add(o4, t, B1);
+    // g2' = 3C - 2 conj(g2) = (3C0 - 2 f2) + (3C1 + 2 f5) s
+    fp2_sub(t, C0, f2); fp2_dbl(t, t); fp2_add(o2, t, C0);
+    fp2_add(t, C1, f5); fp2_dbl(t, t); fp2_add(o5, t, C1);
+    fp12_coef(r, 0) = o0; fp12_coef(r, 1) = o1; fp12_coef(r, 2) = o2;
+    fp12_coef(r, 3) = o3; fp12_coef(r, 4) = o4; fp12_coef(r, 5) = o5;
+}
+
+// Wire format of the reference (A/fp12.rs:859-913): 12 x 48-byte big-endian canonical coefficients in the
+// order w^0, w^3, w^1, w^4, w^2, w^5, each (re, im).
+B3_FN void fp12_to_wire(uint8_t* out, const fp12& a) {
+    const int order[6] = {0, 3, 1, 4, 2, 5};
+    for (int k = 0; k < 6; k++) {
+        const fp2& c = fp12_coef(a, order[k]);
+        fp t;
+        fp_from_mont(t, c.c0);
+        fp_raw_to_be(out + 96 * k, t);
+        fp_from_mont(t, c.c1);
+        fp_raw_to_be(out + 96 * k + 48, t);
+    }
+}
