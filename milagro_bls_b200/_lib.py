@@ -1,0 +1,84 @@
+"""ctypes binding of the C ABI declared in include/milagro_bls_b200.h.
+
+The product has NO CPU path: if the CUDA library is missing, or no sm_100 device is visible, every entry point
+raises.  (The oracle under oracle/ is test infrastructure and is never imported from this package.)
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmilagro_bls_b200.so")
+
+# error codes (include/milagro_bls_b200.h); -1..-8 mirror AmclError (A/errors.rs:1-11)
+OK = 0
+ERR_NAMES = {
+    -1: "AggregateEmptyPoints", -2: "HashToFieldError", -3: "InvalidSecretKeySize", -4: "InvalidSecretKeyRange",
+    -5: "InvalidPoint", -6: "InvalidG1Size", -7: "InvalidG2Size", -8: "InvalidYFlag", -100: "CudaError", -101: "BadArgument",
+}
+PARTIAL_BYTES = 592
+
+
+class B3LibraryMissing(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B3LibraryMissing(
+            f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, sz, i32p, u8p = ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int32), ctypes.c_void_p
+    ip, i64p = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64)
+    sigs = {
+        "b3_ctx_create": ([ctypes.c_int, ctypes.POINTER(vp)], ctypes.c_int),
+        "b3_ctx_destroy": ([vp], None),
+        "b3_last_error": ([vp], ctypes.c_char_p),
+        "b3_ctx_stream": ([vp], vp),
+        "b3_ctx_launch_count": ([vp], ctypes.c_uint64),
+        "b3_ctx_last_kernel_ms": ([vp, ctypes.c_int], ctypes.c_float),
+        "b3_g1_decompress": ([vp, u8p, sz, ctypes.c_int, u8p, i32p], ctypes.c_int),
+        "b3_g2_decompress": ([vp, u8p, sz, u8p, i32p], ctypes.c_int),
+        "b3_g1_compress": ([vp, u8p, sz, u8p, i32p], ctypes.c_int),
+        "b3_g2_compress": ([vp, u8p, sz, u8p, i32p], ctypes.c_int),
+        "b3_g1_validate": ([vp, u8p, sz, i32p, i32p], ctypes.c_int),
+        "b3_g2_subgroup_check": ([vp, u8p, sz, i32p, i32p], ctypes.c_int),
+        "b3_g1_aggregate": ([vp, u8p, vp, sz, u8p, i32p], ctypes.c_int),
+        "b3_g2_aggregate": ([vp, u8p, vp, sz, u8p, i32p], ctypes.c_int),
+        "b3_hash_to_g2": ([vp, u8p, vp, sz, u8p, sz, u8p], ctypes.c_int),
+        "b3_verify": ([vp, u8p, u8p, u8p, sz, ip, u8p], ctypes.c_int),
+        "b3_fast_aggregate_verify": ([vp, u8p, u8p, sz, u8p, sz, ip, u8p], ctypes.c_int),
+        "b3_fast_aggregate_verify_pre_aggregated": ([vp, u8p, u8p, u8p, sz, ip, u8p], ctypes.c_int),
+        "b3_aggregate_verify": ([vp, u8p, u8p, u8p, vp, sz, ip, u8p], ctypes.c_int),
+        "b3_verify_multiple": ([vp, u8p, u8p, vp, u8p, vp, vp, sz, ip, i64p, u8p], ctypes.c_int),
+        "b3_verify_multiple_partial_dev": ([vp, vp, vp, vp, vp, vp, vp, sz, ctypes.c_int64, vp], ctypes.c_int),
+        "b3_combine_partials_dev": ([vp, vp, sz, ip, i64p, u8p], ctypes.c_int),
+        "b3_hash_to_g2_dev": ([vp, vp, vp, sz, vp], ctypes.c_int),
+        "b3_g1_aggregate_dev": ([vp, vp, vp, sz, vp, vp], ctypes.c_int),
+        "b3_g1_mul_gen": ([vp, u8p, sz, u8p], ctypes.c_int),
+        "b3_g2_mul": ([vp, u8p, u8p, sz, u8p], ctypes.c_int),
+        "b3_imad_peak": ([vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double)], ctypes.c_int),
+    }
+    for name, (args, res) in sigs.items():
+        fn = getattr(L, name)          # AttributeError here = header/library mismatch: fail loudly
+        fn.argtypes = args
+        fn.restype = res
+    L._b3_symbols = sorted(sigs)
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "b3_ctx_create", "b3_ctx_destroy", "b3_last_error", "b3_ctx_stream", "b3_ctx_launch_count", "b3_ctx_last_kernel_ms",
+    "b3_g1_decompress", "b3_g2_decompress", "b3_g1_compress", "b3_g2_compress", "b3_g1_validate", "b3_g2_subgroup_check",
+    "b3_g1_aggregate", "b3_g2_aggregate", "b3_hash_to_g2", "b3_verify", "b3_fast_aggregate_verify",
+    "b3_fast_aggregate_verify_pre_aggregated", "b3_aggregate_verify", "b3_verify_multiple",
+    "b3_verify_multiple_partial_dev", "b3_combine_partials_dev", "b3_hash_to_g2_dev", "b3_g1_aggregate_dev",
+    "b3_g1_mul_gen", "b3_g2_mul", "b3_imad_peak",
+]

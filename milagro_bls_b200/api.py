@@ -1,0 +1,520 @@
+"""Host-side mirror of the milagro_bls verification API over the C ABI (include/milagro_bls_b200.h).
+
+Same names, argument meaning and error behaviour as the reference's Rust types (M = /root/reference/src):
+  PublicKey               M/src/keys.rs:116-187        Signature            M/src/signature.rs:9-51
+  AggregatePublicKey      M/src/aggregates.rs:17-78    AggregateSignature   M/src/aggregates.rs:83-334
+Decoding errors raise AmclError(kind) (A/errors.rs:1-11); every verify* returns a plain bool.
+A point is held as its ZCash *uncompressed* encoding (96 B for G1, 192 B for G2) -- the byte string the
+reference's own serialize_uncompressed_g1/g2 produces -- so equality of objects is equality of group elements,
+as with the reference's projective PartialEq.
+
+All arithmetic runs on the GPU through the C ABI.  There is no CPU path here.
+"""
+import ctypes
+import threading
+
+import numpy as np
+
+from . import _lib
+from .rng import draw_scalar
+
+G1_BYTES, G2_BYTES = 48, 96
+G1_INF = bytes([0x40]) + bytes(95)
+G2_INF = bytes([0x40]) + bytes(191)
+
+
+class AmclError(Exception):
+    def __init__(self, kind):
+        super().__init__(kind)
+        self.kind = kind
+
+
+def _raise(code, ctx=None):
+    name = _lib.ERR_NAMES.get(code, f"error {code}")
+    if code <= -100:
+        msg = ""
+        if ctx is not None and ctx.handle:
+            msg = _lib.lib().b3_last_error(ctx.handle).decode(errors="replace")
+        raise RuntimeError(f"milagro_bls_b200: {name} {msg}")
+    raise AmclError(name)
+
+
+def _buf(b):
+    """bytes / bytearray / numpy uint8 array -> (void*, keepalive)"""
+    if isinstance(b, np.ndarray):
+        a = np.ascontiguousarray(b, dtype=np.uint8)
+        return ctypes.c_void_p(a.ctypes.data), a
+    a = np.frombuffer(bytes(b), dtype=np.uint8) if len(b) else np.zeros(1, dtype=np.uint8)
+    return ctypes.c_void_p(a.ctypes.data), a
+
+
+def _offsets(chunks):
+    off = np.zeros(len(chunks) + 1, dtype=np.uint32)
+    if len(chunks):
+        off[1:] = np.cumsum([len(c) for c in chunks], dtype=np.uint64).astype(np.uint32)
+    return off
+
+
+class Engine:
+    """One CUDA context of the library (one per thread / per GPU)."""
+
+    def __init__(self, device=0):
+        self.L = _lib.lib()
+        h = ctypes.c_void_p()
+        rc = self.L.b3_ctx_create(int(device), ctypes.byref(h))
+        self.handle = h if rc == 0 else None
+        if rc != 0:
+            raise RuntimeError(
+                f"milagro_bls_b200: cannot create a context on CUDA device {device} (code {rc}); "
+                "an sm_100 (B200) GPU is required -- there is no CPU fallback")
+        self.device = device
+
+    def close(self):
+        if self.handle:
+            self.L.b3_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- raw batched entry points (numpy in / numpy out) ------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            _raise(rc, self)
+
+    @property
+    def launches(self):
+        return int(self.L.b3_ctx_launch_count(self.handle))
+
+    def last_kernel_ms(self, which=0):
+        return float(self.L.b3_ctx_last_kernel_ms(self.handle, which))
+
+    def g1_decompress(self, data48, validate=True):
+        n = len(data48) // 48
+        p, keep = _buf(data48)
+        out = np.zeros(96 * max(n, 1), dtype=np.uint8)
+        st = np.zeros(max(n, 1), dtype=np.int32)
+        self._ck(self.L.b3_g1_decompress(self.handle, p, n, 1 if validate else 0, out.ctypes.data,
+                                         st.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        return out[:96 * n], st[:n]
+
+    def g2_decompress(self, data96):
+        n = len(data96) // 96
+        p, keep = _buf(data96)
+        out = np.zeros(192 * max(n, 1), dtype=np.uint8)
+        st = np.zeros(max(n, 1), dtype=np.int32)
+        self._ck(self.L.b3_g2_decompress(self.handle, p, n, out.ctypes.data, st.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        return out[:192 * n], st[:n]
+
+    def g1_compress(self, data96):
+        n = len(data96) // 96
+        p, keep = _buf(data96)
+        out = np.zeros(48 * max(n, 1), dtype=np.uint8)
+        st = np.zeros(max(n, 1), dtype=np.int32)
+        self._ck(self.L.b3_g1_compress(self.handle, p, n, out.ctypes.data, st.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        return out[:48 * n], st[:n]
+
+    def g2_compress(self, data192):
+        n = len(data192) // 192
+        p, keep = _buf(data192)
+        out = np.zeros(96 * max(n, 1), dtype=np.uint8)
+        st = np.zeros(max(n, 1), dtype=np.int32)
+        self._ck(self.L.b3_g2_compress(self.handle, p, n, out.ctypes.data, st.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        return out[:96 * n], st[:n]
+
+    def g1_validate(self, data96):
+        n = len(data96) // 96
+        p, keep = _buf(data96)
+        st = np.zeros(max(n, 1), dtype=np.int32)
+        ok = np.zeros(max(n, 1), dtype=np.int32)
+        i32 = ctypes.POINTER(ctypes.c_int32)
+        self._ck(self.L.b3_g1_validate(self.handle, p, n, st.ctypes.data_as(i32), ok.ctypes.data_as(i32)))
+        return st[:n], ok[:n]
+
+    def g2_subgroup_check(self, data192):
+        n = len(data192) // 192
+        p, keep = _buf(data192)
+        st = np.zeros(max(n, 1), dtype=np.int32)
+        ok = np.zeros(max(n, 1), dtype=np.int32)
+        i32 = ctypes.POINTER(ctypes.c_int32)
+        self._ck(self.L.b3_g2_subgroup_check(self.handle, p, n, st.ctypes.data_as(i32), ok.ctypes.data_as(i32)))
+        return st[:n], ok[:n]
+
+    def g1_aggregate(self, pks96, offsets):
+        off = np.ascontiguousarray(offsets, dtype=np.uint32)
+        n = len(off) - 1
+        p, keep = _buf(pks96)
+        out = np.zeros(96 * max(n, 1), dtype=np.uint8)
+        st = np.zeros(max(n, 1), dtype=np.int32)
+        self._ck(self.L.b3_g1_aggregate(self.handle, p, off.ctypes.data, n, out.ctypes.data,
+                                        st.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        return out[:96 * n], st[:n]
+
+    def g2_aggregate(self, sigs192, offsets):
+        off = np.ascontiguousarray(offsets, dtype=np.uint32)
+        n = len(off) - 1
+        p, keep = _buf(sigs192)
+        out = np.zeros(192 * max(n, 1), dtype=np.uint8)
+        st = np.zeros(max(n, 1), dtype=np.int32)
+        self._ck(self.L.b3_g2_aggregate(self.handle, p, off.ctypes.data, n, out.ctypes.data,
+                                        st.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        return out[:192 * n], st[:n]
+
+    def hash_to_g2(self, msgs, dst=None):
+        """msgs: list of bytes -> (n, 192) uint8 array of uncompressed G2 points (M/src/amcl_utils.rs:33-35)."""
+        n = len(msgs)
+        off = _offsets(msgs)
+        p, keep = _buf(b"".join(msgs))
+        out = np.zeros(192 * max(n, 1), dtype=np.uint8)
+        if dst is None:
+            dp, dl, keep2 = None, 0, None
+        else:
+            dp, keep2 = _buf(dst)
+            dl = len(dst)
+        self._ck(self.L.b3_hash_to_g2(self.handle, p, off.ctypes.data, n, dp, dl, out.ctypes.data))
+        return out[:192 * n].reshape(n, 192)
+
+    def verify(self, sig192, pk96, msg, want_gt=False):
+        ok = ctypes.c_int(0)
+        gt = np.zeros(576, dtype=np.uint8)
+        ps, k1 = _buf(sig192)
+        pp, k2 = _buf(pk96)
+        pm, k3 = _buf(msg)
+        self._ck(self.L.b3_verify(self.handle, ps, pp, pm, len(msg), ctypes.byref(ok), gt.ctypes.data))
+        return (bool(ok.value), gt.tobytes()) if want_gt else bool(ok.value)
+
+    def fast_aggregate_verify(self, sig192, pks96, msg, want_gt=False):
+        ok = ctypes.c_int(0)
+        gt = np.zeros(576, dtype=np.uint8)
+        ps, k1 = _buf(sig192)
+        pp, k2 = _buf(pks96)
+        pm, k3 = _buf(msg)
+        self._ck(self.L.b3_fast_aggregate_verify(self.handle, ps, pp, len(pks96) // 96, pm, len(msg), ctypes.byref(ok), gt.ctypes.data))
+        return (bool(ok.value), gt.tobytes()) if want_gt else bool(ok.value)
+
+    def fast_aggregate_verify_pre_aggregated(self, sig192, apk96, msg, want_gt=False):
+        ok = ctypes.c_int(0)
+        gt = np.zeros(576, dtype=np.uint8)
+        ps, k1 = _buf(sig192)
+        pp, k2 = _buf(apk96)
+        pm, k3 = _buf(msg)
+        self._ck(self.L.b3_fast_aggregate_verify_pre_aggregated(self.handle, ps, pp, pm, len(msg), ctypes.byref(ok), gt.ctypes.data))
+        return (bool(ok.value), gt.tobytes()) if want_gt else bool(ok.value)
+
+    def aggregate_verify(self, sig192, pks96, msgs, want_gt=False):
+        ok = ctypes.c_int(0)
+        gt = np.zeros(576, dtype=np.uint8)
+        n = len(msgs)
+        off = _offsets(msgs)
+        ps, k1 = _buf(sig192)
+        pp, k2 = _buf(pks96)
+        pm, k3 = _buf(b"".join(msgs))
+        self._ck(self.L.b3_aggregate_verify(self.handle, ps, pp, pm, off.ctypes.data, n, ctypes.byref(ok), gt.ctypes.data))
+        return (bool(ok.value), gt.tobytes()) if want_gt else bool(ok.value)
+
+    def verify_multiple(self, sigs192, pks96, pk_offsets, msgs_blob, msg_offsets, scalars, want_gt=False):
+        """Raw batched form of verify_multiple_aggregate_signatures.  pk_offsets None -> pks96 holds one
+        (aggregate) key per set.  Returns (accept, first_bad[, gt])."""
+        sc = np.ascontiguousarray(scalars, dtype=np.uint64)
+        n = len(sc)
+        moff = np.ascontiguousarray(msg_offsets, dtype=np.uint32)
+        ok = ctypes.c_int(0)
+        fb = ctypes.c_int64(-1)
+        gt = np.zeros(576, dtype=np.uint8)
+        ps, k1 = _buf(sigs192)
+        pp, k2 = _buf(pks96)
+        pm, k3 = _buf(msgs_blob)
+        if pk_offsets is None:
+            po = None
+        else:
+            koff = np.ascontiguousarray(pk_offsets, dtype=np.uint32)
+            po = koff.ctypes.data
+        self._ck(self.L.b3_verify_multiple(self.handle, ps, pp, po, pm, moff.ctypes.data, sc.ctypes.data, n,
+                                           ctypes.byref(ok), ctypes.byref(fb), gt.ctypes.data))
+        return (bool(ok.value), int(fb.value), gt.tobytes()) if want_gt else (bool(ok.value), int(fb.value))
+
+    # device-pointer forms (torch tensors / raw addresses), used by bench.py and the multi-GPU path
+    def verify_multiple_partial_dev(self, d_sigs, d_pks, d_pk_off, d_msgs, d_msg_off, d_scalars, n, index_base, d_partial):
+        self._ck(self.L.b3_verify_multiple_partial_dev(self.handle, d_sigs, d_pks, d_pk_off, d_msgs, d_msg_off, d_scalars, n,
+                                                       index_base, d_partial))
+
+    def combine_partials_dev(self, d_partials, n_partials, want_gt=False):
+        ok = ctypes.c_int(0)
+        fb = ctypes.c_int64(-1)
+        gt = np.zeros(576, dtype=np.uint8)
+        self._ck(self.L.b3_combine_partials_dev(self.handle, d_partials, n_partials, ctypes.byref(ok), ctypes.byref(fb), gt.ctypes.data))
+        return (bool(ok.value), int(fb.value), gt.tobytes()) if want_gt else (bool(ok.value), int(fb.value))
+
+    def hash_to_g2_dev(self, d_msgs, d_off, n, d_out):
+        self._ck(self.L.b3_hash_to_g2_dev(self.handle, d_msgs, d_off, n, d_out))
+
+    def g1_aggregate_dev(self, d_pks, d_off, n_sets, d_out, d_status):
+        self._ck(self.L.b3_g1_aggregate_dev(self.handle, d_pks, d_off, n_sets, d_out, d_status))
+
+    # signing-side helpers (input synthesis only)
+    def g1_mul_gen(self, scalars):
+        n = len(scalars)
+        blob = b"".join(int(s).to_bytes(32, "big") for s in scalars)
+        p, keep = _buf(blob)
+        out = np.zeros(96 * max(n, 1), dtype=np.uint8)
+        self._ck(self.L.b3_g1_mul_gen(self.handle, p, n, out.ctypes.data))
+        return out[:96 * n].reshape(n, 96)
+
+    def g2_mul(self, pts192, scalars):
+        n = len(scalars)
+        blob = b"".join(int(s).to_bytes(32, "big") for s in scalars)
+        pp, k1 = _buf(pts192)
+        p, keep = _buf(blob)
+        out = np.zeros(192 * max(n, 1), dtype=np.uint8)
+        self._ck(self.L.b3_g2_mul(self.handle, pp, p, n, out.ctypes.data))
+        return out[:192 * n].reshape(n, 192)
+
+    def imad_peak(self, wide=False):
+        v = ctypes.c_double(0)
+        self._ck(self.L.b3_imad_peak(self.handle, 1 if wide else 0, ctypes.byref(v)))
+        return v.value
+
+
+_default = threading.local()
+
+
+def default_engine():
+    e = getattr(_default, "engine", None)
+    if e is None:
+        e = Engine(0)
+        _default.engine = e
+    return e
+
+
+def set_default_engine(e):
+    _default.engine = e
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Reference-shaped types
+# ---------------------------------------------------------------------------------------------------------
+class PublicKey:
+    """M/src/keys.rs:116-187.  `point`: 96-byte uncompressed encoding."""
+    __slots__ = ("point",)
+
+    def __init__(self, point):
+        self.point = bytes(point)
+
+    @staticmethod
+    def from_bytes(data, engine=None):                       # keys.rs:140-147 (validates)
+        return PublicKey._decode(data, True, engine)
+
+    @staticmethod
+    def from_bytes_unchecked(data, engine=None):             # keys.rs:150-155
+        return PublicKey._decode(data, False, engine)
+
+    @staticmethod
+    def _decode(data, validate, engine):
+        data = bytes(data)
+        if len(data) != G1_BYTES:                            # M/src/amcl_utils.rs:52-58
+            raise AmclError("InvalidG1Size")
+        e = engine or default_engine()
+        out, st = e.g1_decompress(data, validate)
+        if st[0]:
+            _raise(int(st[0]))
+        return PublicKey(out.tobytes())
+
+    @staticmethod
+    def from_uncompressed_bytes(data, engine=None):          # keys.rs:168-175
+        data = bytes(data)
+        if len(data) != 2 * G1_BYTES:
+            raise AmclError("InvalidG1Size")
+        e = engine or default_engine()
+        st, _ = e.g1_validate(data)
+        if st[0]:
+            _raise(int(st[0]))
+        return PublicKey(data)
+
+    def as_bytes(self, engine=None):                         # keys.rs:158-160
+        e = engine or default_engine()
+        out, st = e.g1_compress(self.point)
+        if st[0]:
+            _raise(int(st[0]))
+        return out.tobytes()
+
+    def as_uncompressed_bytes(self):                         # keys.rs:163-165
+        return self.point
+
+    def key_validate(self, engine=None):                     # keys.rs:181-186
+        e = engine or default_engine()
+        st, ok = e.g1_validate(self.point)
+        return st[0] == 0 and bool(ok[0])
+
+    def __eq__(self, o):
+        return isinstance(o, PublicKey) and self.point == o.point
+
+    def __hash__(self):
+        return hash(self.point)
+
+
+class AggregatePublicKey:
+    """M/src/aggregates.rs:17-78."""
+    __slots__ = ("point",)
+
+    def __init__(self, point=G1_INF):
+        self.point = bytes(point)
+
+    @staticmethod
+    def aggregate(keys, engine=None):                        # aggregates.rs:29-39
+        return AggregatePublicKey.into_aggregate(keys, engine)
+
+    @staticmethod
+    def into_aggregate(keys, engine=None):                   # aggregates.rs:46-56
+        if len(keys) == 0:
+            raise AmclError("AggregateEmptyPoints")
+        e = engine or default_engine()
+        blob = b"".join(k.point for k in keys)
+        out, st = e.g1_aggregate(blob, [0, len(keys)])
+        if st[0]:
+            _raise(int(st[0]))
+        return AggregatePublicKey(out.tobytes())
+
+    @staticmethod
+    def from_public_key(key):                                # aggregates.rs:61-63
+        return AggregatePublicKey(key.point)
+
+    def add(self, public_key, engine=None):                  # aggregates.rs:68-70
+        e = engine or default_engine()
+        out, st = e.g1_aggregate(self.point + public_key.point, [0, 2])
+        if st[0]:
+            _raise(int(st[0]))
+        self.point = out.tobytes()
+
+    def add_aggregate(self, other, engine=None):             # aggregates.rs:73-77
+        self.add(other, engine)
+
+    def __eq__(self, o):
+        return isinstance(o, AggregatePublicKey) and self.point == o.point
+
+    def __hash__(self):
+        return hash(self.point)
+
+
+class Signature:
+    """M/src/signature.rs:9-51 (verification half; Signature::new needs a secret key and is out of scope)."""
+    __slots__ = ("point",)
+
+    def __init__(self, point):
+        self.point = bytes(point)
+
+    @staticmethod
+    def from_bytes(data, engine=None):                       # signature.rs:43-46 (no subgroup check)
+        data = bytes(data)
+        if len(data) != G2_BYTES:                            # M/src/amcl_utils.rs:68-74
+            raise AmclError("InvalidG2Size")
+        e = engine or default_engine()
+        out, st = e.g2_decompress(data)
+        if st[0]:
+            _raise(int(st[0]))
+        return Signature(out.tobytes())
+
+    def as_bytes(self, engine=None):                         # signature.rs:49-51
+        e = engine or default_engine()
+        out, st = e.g2_compress(self.point)
+        if st[0]:
+            _raise(int(st[0]))
+        return out.tobytes()
+
+    def verify(self, msg, pk, engine=None):                  # signature.rs:27-40
+        e = engine or default_engine()
+        return e.verify(self.point, pk.point, bytes(msg))
+
+    def __eq__(self, o):
+        return isinstance(o, Signature) and self.point == o.point
+
+    def __hash__(self):
+        return hash(self.point)
+
+
+class AggregateSignature:
+    """M/src/aggregates.rs:83-334."""
+    __slots__ = ("point",)
+
+    def __init__(self, point=G2_INF):                        # AggregateSignature::new, aggregates.rs:93-95
+        self.point = bytes(point)
+
+    @staticmethod
+    def aggregate(signatures, engine=None):                  # aggregates.rs:100-106
+        if len(signatures) == 0:
+            return AggregateSignature()
+        e = engine or default_engine()
+        out, st = e.g2_aggregate(b"".join(s.point for s in signatures), [0, len(signatures)])
+        if st[0]:
+            _raise(int(st[0]))
+        return AggregateSignature(out.tobytes())
+
+    @staticmethod
+    def from_signature(signature):                           # aggregates.rs:109-111
+        return AggregateSignature(signature.point)
+
+    def add(self, signature, engine=None):                   # aggregates.rs:114-116
+        e = engine or default_engine()
+        out, st = e.g2_aggregate(self.point + signature.point, [0, 2])
+        if st[0]:
+            _raise(int(st[0]))
+        self.point = out.tobytes()
+
+    def add_aggregate(self, other, engine=None):             # aggregates.rs:119-123
+        self.add(other, engine)
+
+    @staticmethod
+    def from_bytes(data, engine=None):                       # aggregates.rs:319-322
+        return AggregateSignature(Signature.from_bytes(data, engine).point)
+
+    def as_bytes(self, engine=None):                         # aggregates.rs:325-327
+        return Signature(self.point).as_bytes(engine)
+
+    def aggregate_verify(self, msgs, public_keys, engine=None):               # aggregates.rs:130-170
+        if len(msgs) != len(public_keys) or len(public_keys) == 0:
+            return False
+        e = engine or default_engine()
+        return e.aggregate_verify(self.point, b"".join(k.point for k in public_keys), [bytes(m) for m in msgs])
+
+    def fast_aggregate_verify(self, msg, public_keys, engine=None):           # aggregates.rs:177-215
+        if len(public_keys) == 0:
+            return False
+        e = engine or default_engine()
+        return e.fast_aggregate_verify(self.point, b"".join(k.point for k in public_keys), bytes(msg))
+
+    def fast_aggregate_verify_pre_aggregated(self, msg, aggregate_public_key, engine=None):   # aggregates.rs:223-253
+        e = engine or default_engine()
+        return e.fast_aggregate_verify_pre_aggregated(self.point, aggregate_public_key.point, bytes(msg))
+
+    @staticmethod
+    def verify_multiple_aggregate_signatures(rng, signature_sets, engine=None):               # aggregates.rs:261-316
+        """signature_sets: iterable of (AggregateSignature, AggregatePublicKey, msg bytes).
+        `rng`: object with fill(n) -> bytes.  RNG consumption is bit-exact with the reference: one draw per set,
+        in order, and none for / after the first set whose signature fails the subgroup check."""
+        e = engine or default_engine()
+        sets = list(signature_sets)
+        n = len(sets)
+        if n == 0:
+            return True
+        sigs = b"".join(s.point for s, _, _ in sets)
+        st, ok = e.g2_subgroup_check(sigs)
+        for i in range(n):
+            if st[i]:
+                _raise(int(st[i]))
+        bad = [i for i in range(n) if not ok[i]]
+        n_draw = bad[0] if bad else n
+        scalars = [draw_scalar(rng) for _ in range(n_draw)]
+        if bad:
+            return False
+        msgs = [bytes(m) for _, _, m in sets]
+        accept, first_bad = e.verify_multiple(sigs, b"".join(k.point for _, k, _ in sets), None, b"".join(msgs), _offsets(msgs),
+                                              np.array(scalars, dtype=np.uint64))
+        return accept
+
+    def __eq__(self, o):
+        return isinstance(o, AggregateSignature) and self.point == o.point
+
+    def __hash__(self):
+        return hash(self.point)

@@ -1,0 +1,705 @@
+// C ABI (include/milagro_bls_b200.h) and host-side orchestration of the verification path.
+// Single translation unit: the device headers carry __constant__ tables with internal linkage.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/milagro_bls_b200.h"
+#undef B3_OK
+#undef B3_ERR_INVALID_POINT
+#undef B3_ERR_INVALID_YFLAG
+#include "kernels.cuh"
+
+static const uint8_t kDstG2[] = "BLS_SIG_BLS12381G2_XMD:SHA-256_SSWU_RO_POP_";   // A/bls381/proof_of_possession.rs:38
+static const size_t kDstG2Len = 43;
+
+struct dev_buf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct b3_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // 0/1: whole call, 2/3: Miller kernel
+    float last_ms[2] = {0.f, 0.f};
+    // scratch (grown on demand, reused across calls)
+    dev_buf in_a, in_b, in_c, in_d, in_e, in_f;      // staged host inputs
+    dev_buf g1j, g1j2, g1a, g2a_sig, g2j, g2j2, g2a, f12a, f12b, status, ok, misc, outb;
+    uint8_t* d_dst = nullptr;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e);                         \
+            return B3_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+#define CKR(expr)                      \
+    do {                               \
+        int _r = (expr);               \
+        if (_r != B3_OK) return _r;    \
+    } while (0)
+
+static int ensure(b3_ctx* ctx, dev_buf& b, size_t bytes) {
+    if (bytes <= b.cap) return B3_OK;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t cap = bytes + bytes / 4 + 256;
+    CK(cudaMalloc(&b.p, cap));
+    b.cap = cap;
+    return B3_OK;
+}
+static inline unsigned nblk(size_t n, int tpb = B3_TPB) { return (unsigned)((n + tpb - 1) / tpb); }
+#define LAUNCH(kern, grid, block, ...)                       \
+    do {                                                     \
+        kern<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__); \
+        ctx->launches++;                                     \
+    } while (0)
+
+extern "C" int b3_ctx_create(int device, b3_ctx** out) {
+    if (!out) return B3_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return B3_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return B3_ERR_CUDA;
+    if (prop.major != 10) return B3_ERR_CUDA;        // sm_100a code only: no other path exists
+    if (cudaSetDevice(device) != cudaSuccess) return B3_ERR_CUDA;
+    b3_ctx* ctx = new b3_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B3_ERR_CUDA; }
+    for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
+    if (cudaMalloc((void**)&ctx->d_dst, 256) != cudaSuccess) { delete ctx; return B3_ERR_CUDA; }
+    cudaMemcpy(ctx->d_dst, kDstG2, kDstG2Len, cudaMemcpyHostToDevice);
+    *out = ctx;
+    return B3_OK;
+}
+extern "C" void b3_ctx_destroy(b3_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    dev_buf* bufs[] = {&ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->in_d, &ctx->in_e, &ctx->in_f, &ctx->g1j, &ctx->g1j2, &ctx->g1a,
+                       &ctx->g2a_sig, &ctx->g2j, &ctx->g2j2, &ctx->g2a, &ctx->f12a, &ctx->f12b, &ctx->status, &ctx->ok,
+                       &ctx->misc, &ctx->outb};
+    for (dev_buf* b : bufs) if (b->p) cudaFree(b->p);
+    if (ctx->d_dst) cudaFree(ctx->d_dst);
+    for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+extern "C" const char* b3_last_error(b3_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" void* b3_ctx_stream(b3_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" uint64_t b3_ctx_launch_count(b3_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" float b3_ctx_last_kernel_ms(b3_ctx* ctx, int which) { return (ctx && which >= 0 && which < 2) ? ctx->last_ms[which] : 0.f; }
+
+static int h2d(b3_ctx* ctx, dev_buf& b, const void* src, size_t bytes) {
+    CKR(ensure(ctx, b, bytes ? bytes : 1));
+    if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return B3_OK;
+}
+static int d2h(b3_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return B3_OK;
+}
+static int sync(b3_ctx* ctx) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return B3_OK;
+}
+static int begin(b3_ctx* ctx) {
+    if (!ctx) return B3_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return B3_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- generic pieces
+// product of n Fp12 values in `a` (scratch `b`), result left in *res (device pointer into a or b)
+static int fp12_product(b3_ctx* ctx, fp12* a, fp12* b, size_t n, fp12** res) {
+    fp12 *src = a, *dst = b;
+    while (n > 1) {
+        size_t m = (n + 1) / 2;
+        LAUNCH(k_fp12_mul_pairs, nblk(m), B3_TPB, src, n, dst);
+        fp12* t = src; src = dst; dst = t;
+        n = m;
+    }
+    *res = src;
+    return B3_OK;
+}
+static int g2_sum(b3_ctx* ctx, g2_jac* a, g2_jac* b, size_t n, g2_jac** res) {
+    g2_jac *src = a, *dst = b;
+    while (n > 1) {
+        size_t m = (n + 1) / 2;
+        LAUNCH(k_g2_add_pairs, nblk(m), B3_TPB, src, n, dst);
+        g2_jac* t = src; src = dst; dst = t;
+        n = m;
+    }
+    *res = src;
+    return B3_OK;
+}
+// Miller loops over n_pairs (q[i], p[i]) -> product left in *res
+static int miller_product(b3_ctx* ctx, const g2_aff* q, const g1_aff* p, size_t n_pairs, fp12** res) {
+    CKR(ensure(ctx, ctx->f12a, sizeof(fp12) * (n_pairs + 1)));
+    CKR(ensure(ctx, ctx->f12b, sizeof(fp12) * (n_pairs / 2 + 2)));
+    fp12* fa = (fp12*)ctx->f12a.p;
+    if (n_pairs == 0) {
+        LAUNCH(k_fp12_set_one, 1, 1, fa);
+        *res = fa;
+        return B3_OK;
+    }
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    LAUNCH(k_miller, nblk(n_pairs), B3_TPB, q, p, n_pairs, fa);
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    return fp12_product(ctx, fa, (fp12*)ctx->f12b.p, n_pairs, res);
+}
+// final exponentiation of *m -> accept / gt on the host
+static int finish(b3_ctx* ctx, const fp12* m, int* accept, uint8_t* gt576) {
+    CKR(ensure(ctx, ctx->outb, 576 + 16));
+    uint8_t* d_gt = (uint8_t*)ctx->outb.p;
+    int32_t* d_one = (int32_t*)(d_gt + 576);
+    LAUNCH(k_final_exp, 1, 1, m, d_gt, d_one);
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    int32_t one = 0;
+    uint8_t gt[576];
+    CKR(d2h(ctx, &one, d_one, 4));
+    CKR(d2h(ctx, gt, d_gt, 576));
+    CKR(sync(ctx));
+    cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev[0], ctx->ev[1]);
+    if (cudaEventElapsedTime(&ctx->last_ms[1], ctx->ev[2], ctx->ev[3]) != cudaSuccess) ctx->last_ms[1] = 0.f;
+    cudaGetLastError();
+    if (gt576) memcpy(gt576, gt, 576);
+    if (accept) *accept = one ? 1 : 0;
+    return B3_OK;
+}
+// host copy of a status array; returns the first non-zero code or B3_OK
+static int first_status(b3_ctx* ctx, const int32_t* d_status, size_t n) {
+    std::vector<int32_t> h(n);
+    CKR(d2h(ctx, h.data(), d_status, 4 * n));
+    CKR(sync(ctx));
+    for (size_t i = 0; i < n; i++) if (h[i]) return h[i];
+    return B3_OK;
+}
+static int g1_aggregate_dev_impl(b3_ctx* ctx, const uint8_t* d_pks, const uint32_t* d_off, size_t n_sets, size_t total_keys,
+                                 g1_jac* d_out, int32_t* d_status) {
+    if (n_sets == 0) return B3_OK;
+    size_t avg = total_keys / n_sets;
+    // lanes per set: enough lanes to fill the chip, few enough to keep the shuffle tree short
+    if (n_sets >= 16384 || avg <= 8) LAUNCH(k_g1_aggregate<4>, nblk(n_sets * 4), B3_TPB, d_pks, d_off, n_sets, d_out, d_status);
+    else if (n_sets >= 2048 || avg <= 32) LAUNCH(k_g1_aggregate<8>, nblk(n_sets * 8), B3_TPB, d_pks, d_off, n_sets, d_out, d_status);
+    else LAUNCH(k_g1_aggregate<32>, nblk(n_sets * 32), B3_TPB, d_pks, d_off, n_sets, d_out, d_status);
+    return B3_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- serialisation API
+extern "C" int b3_g1_decompress(b3_ctx* ctx, const uint8_t* in48, size_t n, int validate, uint8_t* out96, int32_t* status) {
+    CKR(begin(ctx));
+    if (n == 0) return B3_OK;
+    if (!in48 || !out96 || !status) return B3_ERR_ARG;
+    CKR(h2d(ctx, ctx->in_a, in48, 48 * n));
+    CKR(ensure(ctx, ctx->outb, 96 * n));
+    CKR(ensure(ctx, ctx->status, 4 * n));
+    LAUNCH(k_g1_decompress, nblk(n), B3_TPB, (const uint8_t*)ctx->in_a.p, n, validate, (uint8_t*)ctx->outb.p, (int32_t*)ctx->status.p);
+    CKR(d2h(ctx, out96, ctx->outb.p, 96 * n));
+    CKR(d2h(ctx, status, ctx->status.p, 4 * n));
+    return sync(ctx);
+}
+extern "C" int b3_g2_decompress(b3_ctx* ctx, const uint8_t* in96, size_t n, uint8_t* out192, int32_t* status) {
+    CKR(begin(ctx));
+    if (n == 0) return B3_OK;
+    if (!in96 || !out192 || !status) return B3_ERR_ARG;
+    CKR(h2d(ctx, ctx->in_a, in96, 96 * n));
+    CKR(ensure(ctx, ctx->outb, 192 * n));
+    CKR(ensure(ctx, ctx->status, 4 * n));
+    LAUNCH(k_g2_decompress, nblk(n), B3_TPB, (const uint8_t*)ctx->in_a.p, n, (uint8_t*)ctx->outb.p, (int32_t*)ctx->status.p);
+    CKR(d2h(ctx, out192, ctx->outb.p, 192 * n));
+    CKR(d2h(ctx, status, ctx->status.p, 4 * n));
+    return sync(ctx);
+}
+extern "C" int b3_g1_compress(b3_ctx* ctx, const uint8_t* in96, size_t n, uint8_t* out48, int32_t* status) {
+    CKR(begin(ctx));
+    if (n == 0) return B3_OK;
+    if (!in96 || !out48 || !status) return B3_ERR_ARG;
+    CKR(h2d(ctx, ctx->in_a, in96, 96 * n));
+    CKR(ensure(ctx, ctx->outb, 48 * n));
+    CKR(ensure(ctx, ctx->status, 4 * n));
+    LAUNCH(k_g1_compress, nblk(n), B3_TPB, (const uint8_t*)ctx->in_a.p, n, (uint8_t*)ctx->outb.p, (int32_t*)ctx->status.p);
+    CKR(d2h(ctx, out48, ctx->outb.p, 48 * n));
+    CKR(d2h(ctx, status, ctx->status.p, 4 * n));
+    return sync(ctx);
+}
+extern "C" int b3_g2_compress(b3_ctx* ctx, const uint8_t* in192, size_t n, uint8_t* out96, int32_t* status) {
+    CKR(begin(ctx));
+    if (n == 0) return B3_OK;
+    if (!in192 || !out96 || !status) return B3_ERR_ARG;
+    CKR(h2d(ctx, ctx->in_a, in192, 192 * n));
+    CKR(ensure(ctx, ctx->outb, 96 * n));
+    CKR(ensure(ctx, ctx->status, 4 * n));
+    LAUNCH(k_g2_compress, nblk(n), B3_TPB, (const uint8_t*)ctx->in_a.p, n, (uint8_t*)ctx->outb.p, (int32_t*)ctx->status.p);
+    CKR(d2h(ctx, out96, ctx->outb.p, 96 * n));
+    CKR(d2h(ctx, status, ctx->status.p, 4 * n));
+    return sync(ctx);
+}
+extern "C" int b3_g1_validate(b3_ctx* ctx, const uint8_t* in96, size_t n, int32_t* status, int32_t* valid) {
+    CKR(begin(ctx));
+    if (n == 0) return B3_OK;
+    if (!in96 || !status || !valid) return B3_ERR_ARG;
+    CKR(h2d(ctx, ctx->in_a, in96, 96 * n));
+    CKR(ensure(ctx, ctx->g1j, sizeof(g1_jac) * n));
+    CKR(ensure(ctx, ctx->status, 4 * n));
+    CKR(ensure(ctx, ctx->ok, 4 * n));
+    LAUNCH(k_g1_parse, nblk(n), B3_TPB, (const uint8_t*)ctx->in_a.p, n, (g1_jac*)ctx->g1j.p, (int32_t*)ctx->status.p, 1);
+    LAUNCH(k_g1_key_validate, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j.p, (const int32_t*)ctx->status.p, n, (int32_t*)ctx->ok.p);
+    CKR(d2h(ctx, status, ctx->status.p, 4 * n));
+    CKR(d2h(ctx, valid, ctx->ok.p, 4 * n));
+    return sync(ctx);
+}
+extern "C" int b3_g2_subgroup_check(b3_ctx* ctx, const uint8_t* in192, size_t n, int32_t* status, int32_t* ok) {
+    CKR(begin(ctx));
+    if (n == 0) return B3_OK;
+    if (!in192 || !status || !ok) return B3_ERR_ARG;
+    CKR(h2d(ctx, ctx->in_a, in192, 192 * n));
+    CKR(ensure(ctx, ctx->g2a_sig, sizeof(g2_aff) * n));
+    CKR(ensure(ctx, ctx->status, 4 * n));
+    CKR(ensure(ctx, ctx->ok, 4 * n));
+    LAUNCH(k_g2_parse, nblk(n), B3_TPB, (const uint8_t*)ctx->in_a.p, n, (g2_aff*)ctx->g2a_sig.p, (int32_t*)ctx->status.p, (int32_t*)ctx->ok.p, 1, 1);
+    CKR(d2h(ctx, status, ctx->status.p, 4 * n));
+    CKR(d2h(ctx, ok, ctx->ok.p, 4 * n));
+    return sync(ctx);
+}
+
+// ---------------------------------------------------------------------------------------------- aggregation API
+extern "C" int b3_g1_aggregate_dev(b3_ctx* ctx, const uint8_t* pks96_dev, const uint32_t* off_dev, size_t n_sets, uint8_t* out96_dev,
+                                   int32_t* status_dev) {
+    CKR(begin(ctx));
+    if (n_sets == 0) return B3_OK;
+    CKR(ensure(ctx, ctx->g1j, sizeof(g1_jac) * n_sets));
+    CKR(ensure(ctx, ctx->g1a, sizeof(g1_aff) * n_sets));
+    uint32_t total = 0;
+    CK(cudaMemcpyAsync(&total, off_dev + n_sets, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CKR(sync(ctx));
+    CKR(g1_aggregate_dev_impl(ctx, pks96_dev, off_dev, n_sets, total, (g1_jac*)ctx->g1j.p, status_dev));
+    LAUNCH(k_g1_to_affine, nblk(n_sets), B3_TPB, (const g1_jac*)ctx->g1j.p, n_sets, (g1_aff*)ctx->g1a.p);
+    LAUNCH(k_g1_aff_to_wire, nblk(n_sets), B3_TPB, (const g1_aff*)ctx->g1a.p, n_sets, out96_dev);
+    return sync(ctx);
+}
+extern "C" int b3_g1_aggregate(b3_ctx* ctx, const uint8_t* pks96, const uint32_t* off, size_t n_sets, uint8_t* out96, int32_t* status) {
+    CKR(begin(ctx));
+    if (n_sets == 0) return B3_OK;
+    if (!off || !out96 || !status) return B3_ERR_ARG;
+    size_t total = off[n_sets];
+    CKR(h2d(ctx, ctx->in_a, pks96, 96 * total));
+    CKR(h2d(ctx, ctx->in_b, off, 4 * (n_sets + 1)));
+    CKR(ensure(ctx, ctx->outb, 96 * n_sets));
+    CKR(ensure(ctx, ctx->status, 4 * n_sets));
+    CKR(b3_g1_aggregate_dev(ctx, (const uint8_t*)ctx->in_a.p, (const uint32_t*)ctx->in_b.p, n_sets, (uint8_t*)ctx->outb.p, (int32_t*)ctx->status.p));
+    CKR(d2h(ctx, out96, ctx->outb.p, 96 * n_sets));
+    CKR(d2h(ctx, status, ctx->status.p, 4 * n_sets));
+    return sync(ctx);
+}
+extern "C" int b3_g2_aggregate(b3_ctx* ctx, const uint8_t* sigs192, const uint32_t* off, size_t n_sets, uint8_t* out192, int32_t* status) {
+    CKR(begin(ctx));
+    if (n_sets == 0) return B3_OK;
+    if (!off || !out192 || !status) return B3_ERR_ARG;
+    size_t total = off[n_sets];
+    CKR(h2d(ctx, ctx->in_a, sigs192, 192 * total));
+    CKR(h2d(ctx, ctx->in_b, off, 4 * (n_sets + 1)));
+    CKR(ensure(ctx, ctx->outb, 192 * n_sets));
+    CKR(ensure(ctx, ctx->status, 4 * n_sets));
+    CKR(ensure(ctx, ctx->g2j, sizeof(g2_jac) * n_sets));
+    CKR(ensure(ctx, ctx->g2a, sizeof(g2_aff) * n_sets));
+    size_t avg = total / n_sets;
+    const uint8_t* d_in = (const uint8_t*)ctx->in_a.p;
+    const uint32_t* d_off = (const uint32_t*)ctx->in_b.p;
+    if (n_sets >= 16384 || avg <= 8) LAUNCH(k_g2_aggregate<4>, nblk(n_sets * 4), B3_TPB, d_in, d_off, n_sets, (g2_jac*)ctx->g2j.p, (int32_t*)ctx->status.p);
+    else if (n_sets >= 2048 || avg <= 32) LAUNCH(k_g2_aggregate<8>, nblk(n_sets * 8), B3_TPB, d_in, d_off, n_sets, (g2_jac*)ctx->g2j.p, (int32_t*)ctx->status.p);
+    else LAUNCH(k_g2_aggregate<32>, nblk(n_sets * 32), B3_TPB, d_in, d_off, n_sets, (g2_jac*)ctx->g2j.p, (int32_t*)ctx->status.p);
+    LAUNCH(k_g2_to_affine, nblk(n_sets), B3_TPB, (const g2_jac*)ctx->g2j.p, n_sets, (g2_aff*)ctx->g2a.p);
+    LAUNCH(k_g2_aff_to_wire, nblk(n_sets), B3_TPB, (const g2_aff*)ctx->g2a.p, n_sets, (uint8_t*)ctx->outb.p);
+    CKR(d2h(ctx, out192, ctx->outb.p, 192 * n_sets));
+    CKR(d2h(ctx, status, ctx->status.p, 4 * n_sets));
+    return sync(ctx);
+}
+
+// ---------------------------------------------------------------------------------------------- hash_to_g2 API
+static int stage_dst(b3_ctx* ctx, const uint8_t* dst, size_t dst_len, const uint8_t** d_dst, uint32_t* len) {
+    if (!dst) { *d_dst = ctx->d_dst; *len = (uint32_t)kDstG2Len; return B3_OK; }
+    if (dst_len > 255) return B3_ERR_HASH_TO_FIELD;    // oversize-DST hashing is never reached through milagro_bls
+    CKR(h2d(ctx, ctx->misc, dst, dst_len));
+    *d_dst = (const uint8_t*)ctx->misc.p;
+    *len = (uint32_t)dst_len;
+    return B3_OK;
+}
+static int hash_to_g2_affine_dev(b3_ctx* ctx, const uint8_t* d_msgs, const uint32_t* d_off, size_t n, const uint8_t* d_dst, uint32_t dst_len,
+                                 g2_aff* d_out) {
+    CKR(ensure(ctx, ctx->g2j, sizeof(g2_jac) * n));
+    LAUNCH(k_hash_to_g2, nblk(n), B3_TPB, d_msgs, d_off, n, d_dst, dst_len, (g2_jac*)ctx->g2j.p);
+    LAUNCH(k_g2_to_affine, nblk(n), B3_TPB, (const g2_jac*)ctx->g2j.p, n, d_out);
+    return B3_OK;
+}
+extern "C" int b3_hash_to_g2_dev(b3_ctx* ctx, const uint8_t* msgs_dev, const uint32_t* off_dev, size_t n, uint8_t* out192_dev) {
+    CKR(begin(ctx));
+    if (n == 0) return B3_OK;
+    CKR(ensure(ctx, ctx->g2a, sizeof(g2_aff) * n));
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CKR(hash_to_g2_affine_dev(ctx, msgs_dev, off_dev, n, ctx->d_dst, (uint32_t)kDstG2Len, (g2_aff*)ctx->g2a.p));
+    LAUNCH(k_g2_aff_to_wire, nblk(n), B3_TPB, (const g2_aff*)ctx->g2a.p, n, out192_dev);
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CKR(sync(ctx));
+    cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev[0], ctx->ev[1]);
+    return B3_OK;
+}
+extern "C" int b3_hash_to_g2(b3_ctx* ctx, const uint8_t* msgs, const uint32_t* off, size_t n, const uint8_t* dst, size_t dst_len, uint8_t* out192) {
+    CKR(begin(ctx));
+    if (n == 0) return B3_OK;
+    if (!off || !out192) return B3_ERR_ARG;
+    const uint8_t* d_dst;
+    uint32_t dl;
+    CKR(stage_dst(ctx, dst, dst_len, &d_dst, &dl));
+    CKR(h2d(ctx, ctx->in_a, msgs, off[n]));
+    CKR(h2d(ctx, ctx->in_b, off, 4 * (n + 1)));
+    CKR(ensure(ctx, ctx->g2a, sizeof(g2_aff) * n));
+    CKR(ensure(ctx, ctx->outb, 192 * n));
+    CKR(hash_to_g2_affine_dev(ctx, (const uint8_t*)ctx->in_a.p, (const uint32_t*)ctx->in_b.p, n, d_dst, dl, (g2_aff*)ctx->g2a.p));
+    LAUNCH(k_g2_aff_to_wire, nblk(n), B3_TPB, (const g2_aff*)ctx->g2a.p, n, (uint8_t*)ctx->outb.p);
+    CKR(d2h(ctx, out192, ctx->outb.p, 192 * n));
+    return sync(ctx);
+}
+
+// ---------------------------------------------------------------------------------------------- verification
+// Shared tail of Signature::verify / fast_aggregate_verify* : pairs (sig, -G1), (H(msg), key).
+//   d_sig: parsed signature (g2_aff), d_key: key as g1_jac.  reject_inf_key: the aggregate-key-at-infinity rule.
+static int verify_two_pairs(b3_ctx* ctx, const g2_aff* d_sig, const int32_t* d_sig_ok, const g1_jac* d_key, int reject_inf_key,
+                            const uint8_t* msg, size_t msg_len, int* accept, uint8_t* gt576) {
+    uint32_t off[2] = {0, (uint32_t)msg_len};
+    CKR(h2d(ctx, ctx->in_c, msg, msg_len));
+    CKR(h2d(ctx, ctx->in_d, off, 8));
+    CKR(ensure(ctx, ctx->g2a, sizeof(g2_aff) * 2));
+    CKR(ensure(ctx, ctx->g1a, sizeof(g1_aff) * 2));
+    g2_aff* q = (g2_aff*)ctx->g2a.p;
+    g1_aff* p = (g1_aff*)ctx->g1a.p;
+    // pair 0: (sig, -G1)
+    CK(cudaMemcpyAsync(q, d_sig, sizeof(g2_aff), cudaMemcpyDeviceToDevice, ctx->stream));
+    LAUNCH(k_set_neg_g1, 1, 1, p);
+    // pair 1: (H(msg), key)
+    CKR(hash_to_g2_affine_dev(ctx, (const uint8_t*)ctx->in_c.p, (const uint32_t*)ctx->in_d.p, 1, ctx->d_dst, (uint32_t)kDstG2Len, q + 1));
+    LAUNCH(k_g1_to_affine, 1, B3_TPB, d_key, 1, p + 1);
+    fp12* res;
+    CKR(miller_product(ctx, q, p, 2, &res));
+    int ok = 0;
+    CKR(finish(ctx, res, &ok, gt576));
+    int32_t sig_ok = 0;
+    g1_aff key;
+    CKR(d2h(ctx, &sig_ok, d_sig_ok, 4));
+    CKR(d2h(ctx, &key, p + 1, sizeof(g1_aff)));
+    CKR(sync(ctx));
+    if (!sig_ok) ok = 0;
+    if (reject_inf_key && key.inf) ok = 0;
+    if (accept) *accept = ok;
+    return B3_OK;
+}
+static int parse_sig(b3_ctx* ctx, const uint8_t* sig192) {
+    CKR(h2d(ctx, ctx->in_a, sig192, 192));
+    CKR(ensure(ctx, ctx->g2a_sig, sizeof(g2_aff)));
+    CKR(ensure(ctx, ctx->status, 4 * 4));
+    CKR(ensure(ctx, ctx->ok, 4 * 4));
+    LAUNCH(k_g2_parse, 1, B3_TPB, (const uint8_t*)ctx->in_a.p, 1, (g2_aff*)ctx->g2a_sig.p, (int32_t*)ctx->status.p, (int32_t*)ctx->ok.p, 1, 1);
+    return first_status(ctx, (const int32_t*)ctx->status.p, 1);
+}
+extern "C" int b3_fast_aggregate_verify(b3_ctx* ctx, const uint8_t sig192[192], const uint8_t* pks96, size_t n_pks, const uint8_t* msg,
+                                        size_t msg_len, int* accept, uint8_t* gt576) {
+    CKR(begin(ctx));
+    if (accept) *accept = 0;
+    if (!sig192 || (!msg && msg_len)) return B3_ERR_ARG;
+    if (n_pks == 0) return B3_OK;                       // M/src/aggregates.rs:179-181
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CKR(parse_sig(ctx, sig192));
+    uint32_t off[2] = {0, (uint32_t)n_pks};
+    CKR(h2d(ctx, ctx->in_b, pks96, 96 * n_pks));
+    CKR(h2d(ctx, ctx->in_e, off, 8));
+    CKR(ensure(ctx, ctx->g1j, sizeof(g1_jac) * 2));
+    int32_t* d_st = (int32_t*)ctx->status.p + 1;
+    CKR(g1_aggregate_dev_impl(ctx, (const uint8_t*)ctx->in_b.p, (const uint32_t*)ctx->in_e.p, 1, n_pks, (g1_jac*)ctx->g1j.p, d_st));
+    CKR(first_status(ctx, d_st, 1));
+    return verify_two_pairs(ctx, (const g2_aff*)ctx->g2a_sig.p, (const int32_t*)ctx->ok.p, (const g1_jac*)ctx->g1j.p, 1, msg, msg_len, accept, gt576);
+}
+static int verify_single_key(b3_ctx* ctx, const uint8_t* sig192, const uint8_t* pk96, int reject_inf, const uint8_t* msg, size_t msg_len,
+                             int* accept, uint8_t* gt576) {
+    CKR(begin(ctx));
+    if (accept) *accept = 0;
+    if (!sig192 || !pk96 || (!msg && msg_len)) return B3_ERR_ARG;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CKR(parse_sig(ctx, sig192));
+    CKR(h2d(ctx, ctx->in_b, pk96, 96));
+    CKR(ensure(ctx, ctx->g1j, sizeof(g1_jac) * 2));
+    int32_t* d_st = (int32_t*)ctx->status.p + 1;
+    LAUNCH(k_g1_parse, 1, B3_TPB, (const uint8_t*)ctx->in_b.p, 1, (g1_jac*)ctx->g1j.p, d_st, 1);
+    CKR(first_status(ctx, d_st, 1));
+    return verify_two_pairs(ctx, (const g2_aff*)ctx->g2a_sig.p, (const int32_t*)ctx->ok.p, (const g1_jac*)ctx->g1j.p, reject_inf, msg, msg_len, accept, gt576);
+}
+extern "C" int b3_verify(b3_ctx* ctx, const uint8_t sig192[192], const uint8_t pk96[96], const uint8_t* msg, size_t msg_len, int* accept,
+                         uint8_t* gt576) {
+    return verify_single_key(ctx, sig192, pk96, 0, msg, msg_len, accept, gt576);
+}
+extern "C" int b3_fast_aggregate_verify_pre_aggregated(b3_ctx* ctx, const uint8_t sig192[192], const uint8_t apk96[96], const uint8_t* msg,
+                                                       size_t msg_len, int* accept, uint8_t* gt576) {
+    return verify_single_key(ctx, sig192, apk96, 1, msg, msg_len, accept, gt576);
+}
+
+extern "C" int b3_aggregate_verify(b3_ctx* ctx, const uint8_t sig192[192], const uint8_t* pks96, const uint8_t* msgs, const uint32_t* msg_off,
+                                   size_t n, int* accept, uint8_t* gt576) {
+    CKR(begin(ctx));
+    if (accept) *accept = 0;
+    if (n == 0) return B3_OK;                            // M/src/aggregates.rs:132-134
+    if (!sig192 || !pks96 || !msg_off) return B3_ERR_ARG;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CKR(parse_sig(ctx, sig192));
+    CKR(h2d(ctx, ctx->in_b, pks96, 96 * n));
+    CKR(h2d(ctx, ctx->in_c, msgs, msg_off[n]));
+    CKR(h2d(ctx, ctx->in_d, msg_off, 4 * (n + 1)));
+    CKR(ensure(ctx, ctx->g1j, sizeof(g1_jac) * n));
+    CKR(ensure(ctx, ctx->g1a, sizeof(g1_aff) * (n + 1)));
+    CKR(ensure(ctx, ctx->g2a, sizeof(g2_aff) * (n + 1)));
+    CKR(ensure(ctx, ctx->status, 4 * (n + 4)));
+    int32_t* d_st = (int32_t*)ctx->status.p + 4;
+    LAUNCH(k_g1_parse, nblk(n), B3_TPB, (const uint8_t*)ctx->in_b.p, n, (g1_jac*)ctx->g1j.p, d_st, 1);
+    CKR(first_status(ctx, d_st, n));
+    g2_aff* q = (g2_aff*)ctx->g2a.p;
+    g1_aff* p = (g1_aff*)ctx->g1a.p;
+    LAUNCH(k_g1_to_affine, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j.p, n, p);       // Z = 1: no inversion needed... (generic path)
+    CKR(hash_to_g2_affine_dev(ctx, (const uint8_t*)ctx->in_c.p, (const uint32_t*)ctx->in_d.p, n, ctx->d_dst, (uint32_t)kDstG2Len, q));
+    CK(cudaMemcpyAsync(q + n, ctx->g2a_sig.p, sizeof(g2_aff), cudaMemcpyDeviceToDevice, ctx->stream));
+    LAUNCH(k_set_neg_g1, 1, 1, p + n);
+    fp12* res;
+    CKR(miller_product(ctx, q, p, n + 1, &res));
+    int ok = 0;
+    CKR(finish(ctx, res, &ok, gt576));
+    int32_t sig_ok = 0;
+    CKR(d2h(ctx, &sig_ok, ctx->ok.p, 4));
+    CKR(sync(ctx));
+    if (accept) *accept = (ok && sig_ok) ? 1 : 0;
+    return B3_OK;
+}
+
+// core of verify_multiple on device-resident inputs; leaves this rank's Miller product in *res and the first bad index in d_first_bad
+static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_t* d_pks, const uint32_t* d_pk_off, size_t total_keys,
+                                const uint8_t* d_msgs, const uint32_t* d_msg_off, const uint64_t* d_scalars, size_t n, long long index_base,
+                                fp12** res, long long** d_first_bad_out, int* parse_err) {
+    CKR(ensure(ctx, ctx->g2a_sig, sizeof(g2_aff) * (n + 1)));
+    CKR(ensure(ctx, ctx->status, 4 * (2 * n + 8)));
+    CKR(ensure(ctx, ctx->ok, 4 * (n + 8)));
+    CKR(ensure(ctx, ctx->g1j, sizeof(g1_jac) * (n + 1)));
+    CKR(ensure(ctx, ctx->g1j2, sizeof(g1_jac) * (n + 1)));
+    CKR(ensure(ctx, ctx->g1a, sizeof(g1_aff) * (n + 1)));
+    CKR(ensure(ctx, ctx->g2a, sizeof(g2_aff) * (n + 1)));
+    CKR(ensure(ctx, ctx->g2j2, sizeof(g2_jac) * (n + 2)));
+    CKR(ensure(ctx, ctx->misc, 64));
+    int32_t* d_st_sig = (int32_t*)ctx->status.p;
+    int32_t* d_st_key = d_st_sig + n + 4;
+    long long* d_first_bad = (long long*)ctx->misc.p;
+    long long init = 0x7fffffffffffffffLL;
+    CK(cudaMemcpyAsync(d_first_bad, &init, 8, cudaMemcpyHostToDevice, ctx->stream));
+    g2_aff* q = (g2_aff*)ctx->g2a.p;
+    g1_aff* p = (g1_aff*)ctx->g1a.p;
+    if (n > 0) {
+        // 1. signatures: parse + on-curve + subgroup check (M/src/aggregates.rs:274-276)
+        LAUNCH(k_g2_parse, nblk(n), B3_TPB, d_sigs, n, (g2_aff*)ctx->g2a_sig.p, d_st_sig, (int32_t*)ctx->ok.p, 1, 1);
+        LAUNCH(k_first_bad, nblk(n), B3_TPB, (const int32_t*)ctx->ok.p, n, index_base, d_first_bad);
+        // 2. aggregate public keys
+        if (d_pk_off) CKR(g1_aggregate_dev_impl(ctx, d_pks, d_pk_off, n, total_keys, (g1_jac*)ctx->g1j.p, d_st_key));
+        else LAUNCH(k_g1_parse, nblk(n), B3_TPB, d_pks, n, (g1_jac*)ctx->g1j.p, d_st_key, 1);
+        // 3. P_j = [c_j] apk_j  (M/src/aggregates.rs:293), affine
+        LAUNCH(k_g1_mul_u64, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j.p, d_scalars, n, (g1_jac*)ctx->g1j2.p);
+        LAUNCH(k_g1_to_affine, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j2.p, n, p);
+        // 4. H_j = hash_to_curve_g2(msg_j), affine (M/src/aggregates.rs:290,296)
+        CKR(hash_to_g2_affine_dev(ctx, d_msgs, d_msg_off, n, ctx->d_dst, (uint32_t)kDstG2Len, q));
+        // 5. S = sum_j [c_j] sig_j (M/src/aggregates.rs:303)
+        CKR(ensure(ctx, ctx->g2j, sizeof(g2_jac) * (n + 1)));
+        LAUNCH(k_g2_mul_u64, nblk(n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, d_scalars, n, (g2_jac*)ctx->g2j.p);
+        g2_jac* s;
+        CKR(g2_sum(ctx, (g2_jac*)ctx->g2j.p, (g2_jac*)ctx->g2j2.p, n, &s));
+        LAUNCH(k_g2_to_affine, 1, B3_TPB, (const g2_jac*)s, 1, q + n);
+        LAUNCH(k_set_neg_g1, 1, 1, p + n);
+    }
+    // 6. Miller loops over the n + 1 pairs, product
+    CKR(miller_product(ctx, q, p, n ? n + 1 : 0, res));
+    *d_first_bad_out = d_first_bad;
+    // wire-format errors of the inputs (cannot happen for values that came out of the reference's own types)
+    *parse_err = B3_OK;
+    if (n > 0) {
+        std::vector<int32_t> h(2 * n + 8);
+        CKR(d2h(ctx, h.data(), ctx->status.p, 4 * (2 * n + 8)));
+        CKR(sync(ctx));
+        for (size_t i = 0; i < n && *parse_err == B3_OK; i++) {
+            if (h[i]) *parse_err = h[i];
+            else if (h[n + 4 + i] && h[n + 4 + i] != B3_ERR_AGGREGATE_EMPTY_POINTS) *parse_err = h[n + 4 + i];
+        }
+    }
+    return B3_OK;
+}
+
+extern "C" int b3_verify_multiple(b3_ctx* ctx, const uint8_t* sigs192, const uint8_t* pks96, const uint32_t* pk_off, const uint8_t* msgs,
+                                  const uint32_t* msg_off, const uint64_t* scalars, size_t n, int* accept, int64_t* first_bad, uint8_t* gt576) {
+    CKR(begin(ctx));
+    if (accept) *accept = 0;
+    if (first_bad) *first_bad = -1;
+    if (n && (!sigs192 || !pks96 || !msg_off || !scalars)) return B3_ERR_ARG;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    size_t total_keys = pk_off ? pk_off[n] : n;
+    if (n) {
+        CKR(h2d(ctx, ctx->in_a, sigs192, 192 * n));
+        CKR(h2d(ctx, ctx->in_b, pks96, 96 * total_keys));
+        if (pk_off) CKR(h2d(ctx, ctx->in_e, pk_off, 4 * (n + 1)));
+        CKR(h2d(ctx, ctx->in_c, msgs, msg_off[n]));
+        CKR(h2d(ctx, ctx->in_d, msg_off, 4 * (n + 1)));
+        CKR(h2d(ctx, ctx->in_f, scalars, 8 * n));
+    }
+    fp12* res;
+    long long* d_fb;
+    int perr;
+    CKR(verify_multiple_core(ctx, (const uint8_t*)ctx->in_a.p, (const uint8_t*)ctx->in_b.p, pk_off ? (const uint32_t*)ctx->in_e.p : nullptr,
+                             total_keys, (const uint8_t*)ctx->in_c.p, (const uint32_t*)ctx->in_d.p, (const uint64_t*)ctx->in_f.p, n, 0, &res,
+                             &d_fb, &perr));
+    if (perr) return perr;
+    int ok = 0;
+    CKR(finish(ctx, res, &ok, gt576));
+    long long fb = 0;
+    CKR(d2h(ctx, &fb, d_fb, 8));
+    CKR(sync(ctx));
+    if (fb == 0x7fffffffffffffffLL) fb = -1;
+    if (first_bad) *first_bad = fb;
+    if (accept) *accept = (ok && fb < 0) ? 1 : 0;
+    return B3_OK;
+}
+
+struct partial_rec {
+    fp12 f;
+    long long first_bad;
+    long long pad;
+};
+static_assert(sizeof(partial_rec) == B3_PARTIAL_BYTES, "partial record layout");
+
+__global__ void k_pack_partial(const fp12* f, const long long* fb, partial_rec* out) {
+    out->f = *f;
+    out->first_bad = *fb;
+    out->pad = 0;
+}
+__global__ void k_unpack_partials(const partial_rec* in, size_t n, fp12* f, long long* fb) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    f[i] = in[i].f;
+    atomicMin(fb, in[i].first_bad);
+}
+
+extern "C" int b3_verify_multiple_partial_dev(b3_ctx* ctx, const uint8_t* sigs192_dev, const uint8_t* pks96_dev, const uint32_t* pk_off_dev,
+                                              const uint8_t* msgs_dev, const uint32_t* msg_off_dev, const uint64_t* scalars_dev, size_t n,
+                                              int64_t index_base, uint8_t* partial_dev) {
+    CKR(begin(ctx));
+    if (!partial_dev) return B3_ERR_ARG;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    size_t total_keys = n;
+    if (pk_off_dev && n) {
+        uint32_t t = 0;
+        CK(cudaMemcpyAsync(&t, pk_off_dev + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CKR(sync(ctx));
+        total_keys = t;
+    }
+    fp12* res;
+    long long* d_fb;
+    int perr;
+    CKR(verify_multiple_core(ctx, sigs192_dev, pks96_dev, pk_off_dev, total_keys, msgs_dev, msg_off_dev, scalars_dev, n, index_base, &res, &d_fb,
+                             &perr));
+    if (perr) return perr;
+    LAUNCH(k_pack_partial, 1, 1, (const fp12*)res, (const long long*)d_fb, (partial_rec*)partial_dev);
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CKR(sync(ctx));
+    cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev[0], ctx->ev[1]);
+    if (cudaEventElapsedTime(&ctx->last_ms[1], ctx->ev[2], ctx->ev[3]) != cudaSuccess) ctx->last_ms[1] = 0.f;
+    cudaGetLastError();
+    return B3_OK;
+}
+extern "C" int b3_combine_partials_dev(b3_ctx* ctx, const uint8_t* partials_dev, size_t n_partials, int* accept, int64_t* first_bad,
+                                       uint8_t* gt576) {
+    CKR(begin(ctx));
+    if (accept) *accept = 0;
+    if (first_bad) *first_bad = -1;
+    if (!partials_dev || n_partials == 0) return B3_ERR_ARG;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CKR(ensure(ctx, ctx->f12a, sizeof(fp12) * (n_partials + 1)));
+    CKR(ensure(ctx, ctx->f12b, sizeof(fp12) * (n_partials / 2 + 2)));
+    CKR(ensure(ctx, ctx->misc, 64));
+    long long* d_fb = (long long*)ctx->misc.p;
+    long long init = 0x7fffffffffffffffLL;
+    CK(cudaMemcpyAsync(d_fb, &init, 8, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(k_unpack_partials, nblk(n_partials), B3_TPB, (const partial_rec*)partials_dev, n_partials, (fp12*)ctx->f12a.p, d_fb);
+    fp12* res;
+    CKR(fp12_product(ctx, (fp12*)ctx->f12a.p, (fp12*)ctx->f12b.p, n_partials, &res));
+    int ok = 0;
+    CKR(finish(ctx, res, &ok, gt576));
+    long long fb = 0;
+    CKR(d2h(ctx, &fb, d_fb, 8));
+    CKR(sync(ctx));
+    if (fb == 0x7fffffffffffffffLL) fb = -1;
+    if (first_bad) *first_bad = fb;
+    if (accept) *accept = (ok && fb < 0) ? 1 : 0;
+    return B3_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- signing-side helpers
+extern "C" int b3_g1_mul_gen(b3_ctx* ctx, const uint8_t* scalars32, size_t n, uint8_t* out96) {
+    CKR(begin(ctx));
+    if (n == 0) return B3_OK;
+    if (!scalars32 || !out96) return B3_ERR_ARG;
+    CKR(h2d(ctx, ctx->in_a, scalars32, 32 * n));
+    CKR(ensure(ctx, ctx->outb, 96 * n));
+    LAUNCH(k_g1_mul_gen_u256, nblk(n), B3_TPB, (const uint8_t*)ctx->in_a.p, n, (uint8_t*)ctx->outb.p);
+    CKR(d2h(ctx, out96, ctx->outb.p, 96 * n));
+    return sync(ctx);
+}
+extern "C" int b3_g2_mul(b3_ctx* ctx, const uint8_t* pts192, const uint8_t* scalars32, size_t n, uint8_t* out192) {
+    CKR(begin(ctx));
+    if (n == 0) return B3_OK;
+    if (!pts192 || !scalars32 || !out192) return B3_ERR_ARG;
+    CKR(h2d(ctx, ctx->in_a, pts192, 192 * n));
+    CKR(h2d(ctx, ctx->in_b, scalars32, 32 * n));
+    CKR(ensure(ctx, ctx->outb, 192 * n));
+    LAUNCH(k_g2_mul_u256, nblk(n), B3_TPB, (const uint8_t*)ctx->in_a.p, (const uint8_t*)ctx->in_b.p, n, (uint8_t*)ctx->outb.p);
+    CKR(d2h(ctx, out192, ctx->outb.p, 192 * n));
+    return sync(ctx);
+}
+
+// ---------------------------------------------------------------------------------------------- roofline probe
+extern "C" int b3_imad_peak(b3_ctx* ctx, int wide, double* ops_per_s) {
+    CKR(begin(ctx));
+    if (!ops_per_s) return B3_ERR_ARG;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, ctx->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    CKR(ensure(ctx, ctx->outb, (size_t)blocks * threads * 4));
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+        if (wide) LAUNCH(k_imad_wide_peak, blocks, threads, (uint32_t*)ctx->outb.p, iters, 12345u + rep);
+        else LAUNCH(k_imad_peak, blocks, threads, (uint32_t*)ctx->outb.p, iters, 12345u + rep);
+        CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        CKR(sync(ctx));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        // per thread per iteration: IMAD probe 64 IMADs; wide probe 4*8 = 32 mad.lo/madc.hi PAIRS (= 32 32x32->64 MACs)
+        double ops = (double)blocks * threads * (double)iters * (wide ? 32.0 : 64.0);
+        double rate = ops / (ms * 1e-3);
+        if (rate > best) best = rate;
+    }
+    *ops_per_s = best;
+    return B3_OK;
+}

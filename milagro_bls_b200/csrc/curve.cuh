@@ -20,7 +20,7 @@ B3_FN bool f_is_zero(const fp& a) { return fp_is_zero(a); }
 B3_FN bool f_eq(const fp& a, const fp& b) { return fp_eq(a, b); }
 B3_FN void f_select(fp& r, bool c, const fp& a, const fp& b) { fp_select(r, c, a, b); }
 B3_FN void f_one(fp& r) { r = FP_ONE; }
-B3_FN void f_zero(fp& r) { r = FP_ZERO; }
+B3_FN void f_zero(fp& r) { r = FP_NIL; }
 
 B3_FN void f_add(fp2& r, const fp2& a, const fp2& b) { fp2_add(r, a, b); }
 B3_FN void f_sub(fp2& r, const fp2& a, const fp2& b) { fp2_sub(r, a, b); }
@@ -337,8 +337,8 @@ B3_FN void g2_aff_to_wire(uint8_t* out, const g2_aff& a) {
 }
 // status codes shared with the C ABI (mirror A/errors.rs:1-11)
 #define B3_OK 0
-#define B3_ERR_INVALID_POINT (-4)
-#define B3_ERR_INVALID_YFLAG (-7)
+#define B3_ERR_INVALID_POINT (-5)
+#define B3_ERR_INVALID_YFLAG (-8)
 // Parse without the on-curve check (caller decides); returns B3_OK or an error code.
 B3_FN int g1_aff_from_wire(g1_aff& r, const uint8_t* in) {
     if (in[0] & 0x80) return B3_ERR_INVALID_POINT;          // compressed flag on a 96-byte buffer
@@ -346,7 +346,7 @@ B3_FN int g1_aff_from_wire(g1_aff& r, const uint8_t* in) {
         uint32_t acc = in[0] & 0x3f;
         for (int i = 1; i < 96; i++) acc |= in[i];
         if (acc) return B3_ERR_INVALID_POINT;
-        r.x = FP_ZERO; r.y = FP_ZERO; r.inf = 1;
+        r.x = FP_NIL; r.y = FP_NIL; r.inf = 1;
         return B3_OK;
     }
     if (in[0] & 0x20) return B3_ERR_INVALID_YFLAG;

@@ -237,7 +237,7 @@ B3_FN_NOINLINE void fp_sqr(fp& r, const fp& a) { fp_mul_inl(r, a, a); }
 // Montgomery form <-> canonical
 B3_FN void fp_to_mont(fp& r, const fp& a) { fp_mul(r, FP_R2, a); }       // a any 384-bit value
 B3_FN void fp_from_mont(fp& r, const fp& a) {
-    fp one = FP_ZERO;
+    fp one = FP_NIL;
     one.l[0] = 1;
     fp_mul(r, a, one);
 }

@@ -170,7 +170,7 @@ def fp_arr(name, vs):
 out = ["// GENERATED by gen_constants.py -- do not edit.  Montgomery form, R = 2^384, little-endian u32 limbs.",
        "#pragma once", ""]
 out.append(fp_c("FP_P", p, raw=True))
-out.append(fp_c("FP_ZERO", 0, raw=True))
+out.append(fp_c("FP_NIL", 0, raw=True))
 out.append(fp_c("FP_ONE", 1))
 out.append(fp_c("FP_R2", R % p))                 # mont(R)   = R^2 mod p
 out.append(fp_c("FP_R3", R * R % p))             # mont(R^2) = R^3 mod p

@@ -27,8 +27,8 @@ B3_FN void fp2_conj(fp2& r, const fp2& a) { r.c0 = a.c0; fp_neg(r.c1, a.c1); }
 B3_FN bool fp2_is_zero(const fp2& a) { return fp_is_zero(a.c0) && fp_is_zero(a.c1); }
 B3_FN bool fp2_eq(const fp2& a, const fp2& b) { return fp_eq(a.c0, b.c0) && fp_eq(a.c1, b.c1); }
 B3_FN void fp2_select(fp2& r, bool c, const fp2& a, const fp2& b) { fp_select(r.c0, c, a.c0, b.c0); fp_select(r.c1, c, a.c1, b.c1); }
-B3_FN void fp2_zero(fp2& r) { r.c0 = FP_ZERO; r.c1 = FP_ZERO; }
-B3_FN void fp2_one(fp2& r) { r.c0 = FP_ONE; r.c1 = FP_ZERO; }
+B3_FN void fp2_zero(fp2& r) { r.c0 = FP_NIL; r.c1 = FP_NIL; }
+B3_FN void fp2_one(fp2& r) { r.c0 = FP_ONE; r.c1 = FP_NIL; }
 
 // (a0 + a1 i)(b0 + b1 i), Karatsuba: 3 Fp mults
 B3_FN_NOINLINE void fp2_mul(fp2& r, const fp2& a, const fp2& b) {

@@ -193,9 +193,9 @@ def test_g1_ops(hs):
     assert hs.hs_g1_check(g1w((1, 1)), ctypes.byref(oc), ctypes.byref(sg)) == 0 and oc.value == 0
     assert hs.hs_g1_check(g1w(None), ctypes.byref(oc), ctypes.byref(sg)) == 0 and sg.value == 1
     bad = bytearray(g1w(A)); bad[0] |= 0x20
-    assert hs.hs_g1_check(bytes(bad), ctypes.byref(oc), ctypes.byref(sg)) == -7
-    assert hs.hs_g1_check(b"\x1f" + b"\xff" * 95, ctypes.byref(oc), ctypes.byref(sg)) == -4
-    assert hs.hs_g1_check(b"\x40" + b"\x00" * 94 + b"\x01", ctypes.byref(oc), ctypes.byref(sg)) == -4
+    assert hs.hs_g1_check(bytes(bad), ctypes.byref(oc), ctypes.byref(sg)) == -8
+    assert hs.hs_g1_check(b"\x1f" + b"\xff" * 95, ctypes.byref(oc), ctypes.byref(sg)) == -5
+    assert hs.hs_g1_check(b"\x40" + b"\x00" * 94 + b"\x01", ctypes.byref(oc), ctypes.byref(sg)) == -5
 
 
 def test_g2_ops(hs):
