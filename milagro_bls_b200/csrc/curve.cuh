@@ -178,7 +178,7 @@ B3_FN_NOINLINE void pt_add_aff(jac<F>& r, const jac<F>& p, const aff<F>& q) {
 }
 
 template <class F>
-B3_FN void pt_to_aff(aff<F>& r, const jac<F>& p) {
+B3_FN_NOINLINE void pt_to_aff(aff<F>& r, const jac<F>& p) {
     if (pt_is_inf(p)) { f_zero(r.x); f_zero(r.y); r.inf = 1; return; }
     F zi, zi2;
     f_inv(zi, p.z);
@@ -191,7 +191,7 @@ B3_FN void pt_to_aff(aff<F>& r, const jac<F>& p) {
 
 // projective equality (reference: A/ecp.rs:339-357, A/ecp2.rs:182-200)
 template <class F>
-B3_FN bool pt_eq(const jac<F>& a, const jac<F>& b) {
+B3_FN_NOINLINE bool pt_eq(const jac<F>& a, const jac<F>& b) {
     bool ai = pt_is_inf(a), bi = pt_is_inf(b);
     if (ai || bi) return ai && bi;
     F za, zb, t0, t1;
@@ -209,7 +209,7 @@ B3_FN bool pt_eq(const jac<F>& a, const jac<F>& b) {
 
 // y^2 == x^3 + b
 template <class F>
-B3_FN bool pt_on_curve_aff(const aff<F>& a) {
+B3_FN_NOINLINE bool pt_on_curve_aff(const aff<F>& a) {
     if (a.inf) return true;
     F l, rr, one;
     f_sqr(l, a.y);
@@ -266,7 +266,7 @@ B3_FN_NOINLINE void pt_mul_u256_aff(jac<F>& r, const aff<F>& p, const uint32_t* 
 // ---- endomorphisms ------------------------------------------------------------------------------
 // psi on G2 (untwist-Frobenius-twist), Jacobian: (conj X * cx, conj Y * cy, conj Z)
 //   reference: A/ecp2.rs:538-548 with X = 1/FROB (A/ecp2.rs:785-789)
-B3_FN void g2_psi(g2_jac& r, const g2_jac& p) {
+B3_FN_NOINLINE void g2_psi(g2_jac& r, const g2_jac& p) {
     fp2 t;
     fp2_conj(t, p.x); fp2_mul(r.x, t, PSI_CX);
     fp2_conj(t, p.y); fp2_mul(r.y, t, PSI_CY);
@@ -283,7 +283,7 @@ B3_FN void g1_phi(g1_jac& r, const g1_jac& p) { fp_mul(r.x, p.x, FP_BETA); r.y =
 // Subgroup membership.  The reference tests [r]P == O through its GLV/GS ladders
 // (A/bls381/core.rs:116-127 -> A/pair.rs:625-693); any exact membership test gives the same answer on
 // every on-curve input.  G2: psi(P) == [x]P = -[|x|]P.  G1: phi(P) == [-x^2]P.
-B3_FN bool g2_in_subgroup(const g2_jac& p) {
+B3_FN_NOINLINE bool g2_in_subgroup(const g2_jac& p) {
     if (pt_is_inf(p)) return true;
     g2_jac xp, ps;
     pt_mul_u64(xp, p, B3_X_ABS);
@@ -291,7 +291,7 @@ B3_FN bool g2_in_subgroup(const g2_jac& p) {
     g2_psi(ps, p);
     return pt_eq(xp, ps);
 }
-B3_FN bool g1_in_subgroup(const g1_jac& p) {
+B3_FN_NOINLINE bool g1_in_subgroup(const g1_jac& p) {
     if (pt_is_inf(p)) return true;
     g1_jac t, ph;
     pt_mul_u64(t, p, B3_X_ABS);
@@ -321,13 +321,13 @@ B3_FN_NOINLINE void g2_clear_cofactor(g2_jac& r, const g2_jac& p) {
 
 // ---- wire formats (ZCash uncompressed; A/bls381/core.rs:177-190, 344-364) -----------------------
 // G1: x || y (48-byte big-endian each); G2: x.im || x.re || y.im || y.re; infinity = 0x40 then zeros.
-B3_FN void g1_aff_to_wire(uint8_t* out, const g1_aff& a) {
+B3_FN_NOINLINE void g1_aff_to_wire(uint8_t* out, const g1_aff& a) {
     if (a.inf) { for (int i = 0; i < 96; i++) out[i] = 0; out[0] = 0x40; return; }
     fp t;
     fp_from_mont(t, a.x); fp_raw_to_be(out, t);
     fp_from_mont(t, a.y); fp_raw_to_be(out + 48, t);
 }
-B3_FN void g2_aff_to_wire(uint8_t* out, const g2_aff& a) {
+B3_FN_NOINLINE void g2_aff_to_wire(uint8_t* out, const g2_aff& a) {
     if (a.inf) { for (int i = 0; i < 192; i++) out[i] = 0; out[0] = 0x40; return; }
     fp t;
     fp_from_mont(t, a.x.c1); fp_raw_to_be(out, t);
@@ -340,7 +340,7 @@ B3_FN void g2_aff_to_wire(uint8_t* out, const g2_aff& a) {
 #define B3_ERR_INVALID_POINT (-5)
 #define B3_ERR_INVALID_YFLAG (-8)
 // Parse without the on-curve check (caller decides); returns B3_OK or an error code.
-B3_FN int g1_aff_from_wire(g1_aff& r, const uint8_t* in) {
+B3_FN_NOINLINE int g1_aff_from_wire(g1_aff& r, const uint8_t* in) {
     if (in[0] & 0x80) return B3_ERR_INVALID_POINT;          // compressed flag on a 96-byte buffer
     if (in[0] & 0x40) {
         uint32_t acc = in[0] & 0x3f;
@@ -357,7 +357,7 @@ B3_FN int g1_aff_from_wire(g1_aff& r, const uint8_t* in) {
     fp_to_mont(r.x, x); fp_to_mont(r.y, y); r.inf = 0;
     return B3_OK;
 }
-B3_FN int g2_aff_from_wire(g2_aff& r, const uint8_t* in) {
+B3_FN_NOINLINE int g2_aff_from_wire(g2_aff& r, const uint8_t* in) {
     if (in[0] & 0x80) return B3_ERR_INVALID_POINT;
     if (in[0] & 0x40) {
         uint32_t acc = in[0] & 0x3f;

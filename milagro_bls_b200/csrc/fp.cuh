@@ -95,6 +95,10 @@ B3_FN void madc_wide_last(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
 }
 #endif
 
+// NOTE (nvcc 12.9): an inline helper that owns fp-sized locals whose addresses are passed to __noinline__
+// functions gets its stack slots mis-merged when it is inlined more than once into one caller (observed:
+// two live temporaries of sswu_g2 sharing one slot, tests/hostsim/dbg_sswu.py).  Rule used throughout: such
+// helpers are __noinline__ themselves; only helpers without address-taken locals are force-inlined.
 // ------------------------------------------------------------------------------------------------
 // basic predicates / moves
 // ------------------------------------------------------------------------------------------------
@@ -236,11 +240,7 @@ B3_FN_NOINLINE void fp_sqr(fp& r, const fp& a) { fp_mul_inl(r, a, a); }
 
 // Montgomery form <-> canonical
 B3_FN void fp_to_mont(fp& r, const fp& a) { fp_mul(r, FP_R2, a); }       // a any 384-bit value
-B3_FN void fp_from_mont(fp& r, const fp& a) {
-    fp one = FP_NIL;
-    one.l[0] = 1;
-    fp_mul(r, a, one);
-}
+B3_FN void fp_from_mont(fp& r, const fp& a) { fp_mul(r, a, FP_RAW_ONE); }
 
 // r = a^e for a fixed public exponent e (plain 384-bit integer), 4-bit fixed window
 B3_FN_NOINLINE void fp_pow_const(fp& r, const fp& a, const fp& e) {
@@ -269,7 +269,7 @@ B3_FN void fp_inv(fp& r, const fp& a) { fp_pow_const(r, a, FP_EXP_INV); }   // 0
 //   t = g*d, chi = t*g = d^((p-1)/2) in {0, 1, -1}.  If chi == 1: t^2 = d and 1/t = g.
 //   If chi == -1: t^2 = -d and 1/t = -g.
 // Returns is_qr (chi != -1), t and tinv = g*chi.
-B3_FN bool fp_sqrt_ratio_parts(fp& t, fp& tinv, const fp& d) {
+B3_FN_NOINLINE bool fp_sqrt_ratio_parts(fp& t, fp& tinv, const fp& d) {
     fp g, chi;
     fp_pow_const(g, d, FP_EXP_SQRT_G);
     fp_mul(t, g, d);

@@ -109,7 +109,7 @@ B3_FN_NOINLINE void expand_message_xmd_256(uint32_t* out64, const uint8_t* msg, 
     }
 }
 // 64 big-endian bytes (16 BE words) -> Fp element in Montgomery form: OS2IP(bytes) mod p
-B3_FN void fp_from_be64_words(fp& r, const uint32_t* w16) {
+B3_FN_NOINLINE void fp_from_be64_words(fp& r, const uint32_t* w16) {
     fp lo, hi, t;
     for (int i = 0; i < 12; i++) lo.l[i] = w16[15 - i];
     for (int i = 0; i < 4; i++) hi.l[i] = w16[3 - i];
@@ -118,7 +118,7 @@ B3_FN void fp_from_be64_words(fp& r, const uint32_t* w16) {
     fp_mul(t, FP_R3, hi);           // hi * 2^384 * R
     fp_add(r, lo, t);
 }
-B3_FN void hash_to_field_fp2_x2(fp2& u0, fp2& u1, const uint8_t* msg, uint32_t msg_len, const uint8_t* dst, uint32_t dst_len) {
+B3_FN_NOINLINE void hash_to_field_fp2_x2(fp2& u0, fp2& u1, const uint8_t* msg, uint32_t msg_len, const uint8_t* dst, uint32_t dst_len) {
     uint32_t prb[64];
     expand_message_xmd_256(prb, msg, msg_len, dst, dst_len);
     fp_from_be64_words(u0.c0, prb);
@@ -132,7 +132,7 @@ B3_FN void hash_to_field_fp2_x2(fp2& u0, fp2& u1, const uint8_t* msg, uint32_t m
 //   tv1 = Z u^2, tv2 = tv1^2 + tv1, x1 = (-B/A)(1 + 1/tv2) = -B (tv2 + 1) / (A tv2)   (tv2 == 0: x1 = B/(Z A))
 //   gx1 = (xn^3 + A xn xd^2 + B xd^3) / xd^3;  y1 = sqrt(gx1) or, if gx1 is not a square,
 //   x2 = tv1 x1 and y2 = tv1 u sqrt(Z gx1)     (RFC 9380 F.2 straight-line version)
-B3_FN_NOINLINE void sswu_g2(fp2& xn, fp2& xd, fp2& y, const fp2& u) {
+B3_FN_NOINLINE void sswu_g2(fp2& xn, fp2& xd, fp2& y, const fp2& u, fp2* dbg = nullptr) {
     fp2 tv1, tv2, gxn, gxd, t, t2;
     fp2_sqr(tv1, u);
     fp2_mul(tv1, tv1, SSWU_Z);
@@ -170,13 +170,18 @@ B3_FN_NOINLINE void sswu_g2(fp2& xn, fp2& xd, fp2& y, const fp2& u) {
     bool sq = fp2_sqrt_or_z(root, wv);          // sqrt(W) or sqrt(Z W)
     fp ninv;
     fp_inv(ninv, n);
+    if (dbg) dbg[0] = root;
     fp2_mul_fp(root, root, ninv);               // sqrt(gx1) or sqrt(Z gx1)
+    if (dbg) dbg[1] = root;
     if (!sq) {
         fp2_mul(xn, xn, tv1);                   // x2 = tv1 x1
         fp2_mul(t, tv1, u);
+        if (dbg) dbg[2] = t;
         fp2_mul(root, root, t);                 // y2 = tv1 u sqrt(Z gx1)
     }
+    if (dbg) dbg[3] = root;
     if (fp2_sgn0(u) != fp2_sgn0(root)) fp2_neg(root, root);
+    if (dbg) dbg[4] = root;
     y = root;
 }
 
@@ -229,7 +234,7 @@ B3_FN_NOINLINE void iso3_g2(g2_jac& r, const fp2& xn, const fp2& xd, const fp2& 
     r.z = z;
 }
 
-B3_FN void map_to_curve_g2(g2_jac& r, const fp2& u) {
+B3_FN_NOINLINE void map_to_curve_g2(g2_jac& r, const fp2& u) {
     fp2 xn, xd, y;
     sswu_g2(xn, xd, y, u);
     iso3_g2(r, xn, xd, y);

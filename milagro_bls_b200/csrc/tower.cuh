@@ -72,7 +72,7 @@ B3_FN_NOINLINE void fp2_inv(fp2& r, const fp2& a) {
     fp_neg(r.c1, t);
 }
 // RFC 9380 sgn0 for m = 2 (= reference A/fp2.rs:449-455); input in Montgomery form
-B3_FN uint32_t fp2_sgn0(const fp2& a) {
+B3_FN_NOINLINE uint32_t fp2_sgn0(const fp2& a) {
     fp r0, r1;
     fp_from_mont(r0, a.c0);
     fp_from_mont(r1, a.c1);
@@ -305,7 +305,7 @@ B3_FN_NOINLINE void fp12_frob3(fp12& r, const fp12& a) {
 
 // Granger-Scott squaring for elements of the cyclotomic subgroup (after the easy part of fexp).
 // Uses the Fp4 = Fp2[s]/(s^2 - xi) sub-structure with s = w^3: pairs (f0,f3), (f1,f4), (f2,f5).
-B3_FN void fp4_sqr_parts(fp2& r0, fp2& r1, const fp2& a, const fp2& b) {
+B3_FN_NOINLINE void fp4_sqr_parts(fp2& r0, fp2& r1, const fp2& a, const fp2& b) {
     // (a + b s)^2 = (a^2 + xi b^2) + (2ab) s
     fp2 t0, t1, t2;
     fp2_sqr(t0, a);
@@ -347,7 +347,7 @@ B3_FN_NOINLINE void fp12_cyclo_sqr(fp12& r, const fp12& a) {
 
 // Wire format of the reference (A/fp12.rs:859-913): 12 x 48-byte big-endian canonical coefficients in the
 // order w^0, w^3, w^1, w^4, w^2, w^5, each (re, im).
-B3_FN void fp12_to_wire(uint8_t* out, const fp12& a) {
+B3_FN_NOINLINE void fp12_to_wire(uint8_t* out, const fp12& a) {
     const int order[6] = {0, 3, 1, 4, 2, 5};
     for (int k = 0; k < 6; k++) {
         const fp2& c = fp12_coef(a, order[k]);

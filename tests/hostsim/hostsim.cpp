@@ -53,7 +53,10 @@ int hs_fp2_sqrt_or_z(const uint8_t* a, uint8_t* out) {
     fp2_out(out, r);
     return sq ? 1 : 0;
 }
-int hs_fp2_sgn0(const uint8_t* a) { fp2 x; fp2_in(x, a); return (int)fp2_sgn0(x); }
+int hs_fp2_sgn0(const uint8_t* a) {
+    fp2 x; fp2_in(x, a);
+    return (int)fp2_sgn0(x);
+}
 // op: 0 mul, 1 sqr, 2 inv, 3 frob, 4 frob2, 5 frob3, 6 conj, 7 cyclo_sqr, 8 final_exp, 9 pow_x
 void hs_fp12_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     fp12 x, y, r;
@@ -81,6 +84,94 @@ void hs_hash_to_field(const uint8_t* msg, uint32_t len, const uint8_t* dst, uint
 void hs_map_to_curve_g2(const uint8_t* u96, uint8_t* out192) {
     fp2 u; fp2_in(u, u96);
     g2_jac q; map_to_curve_g2(q, u);
+    g2_aff a; pt_to_aff(a, q);
+    g2_aff_to_wire(out192, a);
+}
+void hs_sswu(const uint8_t* u96, uint8_t* out288) {
+    fp2 u, xn, xd, y; fp2_in(u, u96);
+    sswu_g2(xn, xd, y, u);
+    fp2_out(out288, xn); fp2_out(out288 + 96, xd); fp2_out(out288 + 192, y);
+}
+// debug: intermediates of sswu_g2 (same statements, exported one by one)
+void hs_sswu_dbg(const uint8_t* u96, uint8_t* outdbg) {
+    uint8_t* out = outdbg;
+    fp2 u; fp2_in(u, u96);
+    fp2 tv1, tv2, gxn, gxd, t, t2, xn, xd;
+    fp2_sqr(tv1, u);
+    fp2_mul(tv1, tv1, SSWU_Z);
+    fp2_sqr(tv2, tv1);
+    fp2_add(tv2, tv2, tv1);
+    bool exc = fp2_is_zero(tv2);
+    fp2 one; fp2_one(one);
+    fp2_add(t, tv2, one);
+    fp2_mul(t, t, SSWU_B);
+    fp2_neg(t, t);
+    fp2_select(xn, exc, SSWU_B, t);
+    fp2_mul(t, tv2, SSWU_A);
+    fp2_select(xd, exc, SSWU_ZA, t);
+    fp2_sqr(t, xd);
+    fp2_mul(gxd, t, xd);
+    fp2_mul(t, t, SSWU_A);
+    fp2_sqr(t2, xn);
+    fp2_add(t, t, t2);
+    fp2_mul(t, t, xn);
+    fp2_mul(t2, gxd, SSWU_B);
+    fp2_add(gxn, t, t2);
+    fp n, s2;
+    fp_sqr(n, gxd.c0);
+    fp_sqr(s2, gxd.c1);
+    fp_add(n, n, s2);
+    fp2 wv, root;
+    fp2_conj(t, gxd);
+    fp2_mul(wv, gxn, t);
+    fp2_mul_fp(wv, wv, n);
+    bool sq = fp2_sqrt_or_z(root, wv);
+    fp ninv;
+    fp_inv(ninv, n);
+    fp2 root2;
+    fp2_mul_fp(root2, root, ninv);
+    fp2_out(out, tv1); fp2_out(out + 96, gxn); fp2_out(out + 192, gxd);
+    fp_out(out + 288, n); fp2_out(out + 336, wv); fp2_out(out + 432, root);
+    fp_out(out + 528, ninv); fp2_out(out + 576, root2);
+    out[672] = sq ? 1 : 0; out[673] = (uint8_t)fp2_sgn0(u); out[674] = (uint8_t)fp2_sgn0(root2);
+    // tail
+    fp2 tt, root3 = root2, root4;
+    if (!sq) {
+        fp2_mul(tt, tv1, u);
+        fp2_mul(root3, root3, tt);
+    }
+    fp2_out(out + 700, root3);
+    out[675] = (uint8_t)fp2_sgn0(root3);
+    root4 = root3;
+    if (fp2_sgn0(u) != fp2_sgn0(root4)) fp2_neg(root4, root4);
+    fp2_out(out + 800, root4);
+    fp2 rxn, rxd, ry;
+    fp2 dbgv[5];
+    sswu_g2(rxn, rxd, ry, u, dbgv);
+    fp2_out(out + 900, ry);
+    out[682] = fp2_eq(dbgv[0], root); out[683] = fp2_eq(dbgv[1], root2); out[684] = fp2_eq(dbgv[3], root3); out[685] = fp2_eq(dbgv[4], root4);
+    out[686] = fp2_eq(dbgv[4], ry);
+    // variant A: in-place scaling like the real function
+    fp2 ra = root;
+    fp2_mul_fp(ra, ra, ninv);
+    out[676] = fp2_eq(ra, root2) ? 1 : 0;
+    // variant B: in-place xn update + t reuse
+    fp2 xb = xn;
+    if (!sq) {
+        fp2_mul(xb, xb, tv1);
+        fp2_mul(t, tv1, u);
+        fp2_mul(ra, ra, t);
+    }
+    out[677] = fp2_eq(ra, root3) ? 1 : 0;
+    if (fp2_sgn0(u) != fp2_sgn0(ra)) fp2_neg(ra, ra);
+    out[678] = fp2_eq(ra, root4) ? 1 : 0;
+    out[679] = fp2_eq(ry, root4) ? 1 : 0;
+    out[680] = fp2_eq(rxn, xb) ? 1 : 0;
+    out[681] = fp2_eq(rxd, xd) ? 1 : 0;
+}
+void hs_iso3(const uint8_t* in288, uint8_t* out192) {
+    fp2 xn, xd, y; fp2_in(xn, in288); fp2_in(xd, in288 + 96); fp2_in(y, in288 + 192);
+    g2_jac q; iso3_g2(q, xn, xd, y);
     g2_aff a; pt_to_aff(a, q);
     g2_aff_to_wire(out192, a);
 }

@@ -159,6 +159,20 @@ def test_hash_to_field_and_map(hs):
         assert out.raw == O.serialize_uncompressed_g2(O.map_to_curve_g2(u)), u
 
 
+def test_sswu_and_iso3(hs):
+    for u in [rfp2() for _ in range(12)] + [(0, 0), (1, 0), (0, 1)]:
+        out = ctypes.create_string_buffer(288)
+        hs.hs_sswu(fp2b(u), out)
+        xn, xd, y = bfp2(out.raw[:96]), bfp2(out.raw[96:192]), bfp2(out.raw[192:])
+        x = O.f2_mul(xn, O.f2_inv(xd))
+        xo, yo = O.simplified_swu_fp2(u)
+        assert x == xo, u
+        assert y == yo, u
+        o2 = ctypes.create_string_buffer(192)
+        hs.hs_iso3(fp2b(xo) + fp2b((1, 0)) + fp2b(yo), o2)
+        assert o2.raw == O.serialize_uncompressed_g2(O.iso3_to_ecp2(xo, yo)), u
+
+
 def test_hash_to_g2(hs):
     for msg in [b"", b"abc", b"cats", bytes([7]) * 32]:
         out = ctypes.create_string_buffer(192)
