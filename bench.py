@@ -1,0 +1,354 @@
+#!/usr/bin/env python3
+"""bench.py -- verified signature-sets/s of verify_multiple_aggregate_signatures on B200.
+
+Contract (see the task statement):  python bench.py --gpus N --steps K --warmup W [--impl reference]
+  * workload at N = 1: BASELINE.json configs[3] -- 8192 attestation sets x 128 public keys, distinct random
+    32-byte messages, 63-bit batch scalars (C4).  For N > 1 every rank keeps 8192 sets (weak scaling), so N = 8
+    is BASELINE.json configs[4] (2^16 sets, NCCL combine of the 592-byte partial Miller products).
+  * a step = one full verification of the batch: G2 subgroup checks, G1 key aggregation, [c]apk, hash_to_G2,
+    [c]sig sum, n+1 Miller loops, Fp12 product, (all-gather,) one final exponentiation, accept bit.
+  * value  = sets verified per second, inputs resident in HBM (device-pointer C-ABI entry points).
+  * e2e    = same metric through the host-pointer C-ABI call (b3_verify_multiple) with pinned HOST buffers:
+             H2D of the step's inputs and D2H of accept + GT inside the timed region.
+  * roofline: bound = integer multiply pipe (IMAD); the peak is measured live with a pure IMAD.WIDE carry-chain
+    probe (b3_imad_peak); HBM figures are reported next to it to show that memory is not binding.
+  * cpu_baseline / --impl reference: the reference's CPU algorithm (oracle/ C restatement; the Rust crate cannot be
+    built here -- no rustc) on all host cores, on a bounded sample of the same workload.
+Only this file's cpu_baseline / --impl reference legs touch oracle/ -- never the measured GPU path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SETS_PER_GPU = 8192
+KEYS_PER_SET = 128
+POOL = 16384
+MSG_LEN = 32
+R_ORDER = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+# algorithmic work per unit: 32x32->64 multiply-accumulates, 300 per Fp multiplication
+MACS_PER_FP_MUL = 300
+FP_MULS = {"g1_aggregate": 1400, "g2_parse_subgroup_check": 1170, "hash_to_g2_affine": 6700, "g1_scalar_mul_affine": 670 + 15,
+           "g2_scalar_mul_sum": 1650, "miller_loop": 4800, "fp12_product_tree": 54, "final_exp": 0}
+FP_MULS_PER_SET = 16400
+BYTES_PER_SET = KEYS_PER_SET * 96 + 192 + MSG_LEN + 8          # algorithmic HBM bytes read per set
+
+
+def splitmix64(seed):
+    x = seed & (2**64 - 1)
+    while True:
+        x = (x + 0x9E3779B97F4A7C15) & (2**64 - 1)
+        z = x
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2**64 - 1)
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2**64 - 1)
+        yield z ^ (z >> 31)
+
+
+def synth_inputs(eng, n_sets, n_keys, seed, rank=0):
+    """Synthetic, VALID signature sets.  Signing-side work (pk = [sk]G1,
+    sig = [sum sk]H(m)) runs on the GPU helpers b3_g1_mul_gen / b3_g2_mul; it is input synthesis, not timed."""
+    import numpy as np
+    g = splitmix64(seed)
+    sks = [1 + ((next(g) | (next(g) << 64) | (next(g) << 128) | (next(g) << 192)) % (R_ORDER - 1)) for _ in range(POOL)]
+    pool = eng.g1_mul_gen(sks)                                   # (POOL, 96)
+    rs = np.random.RandomState((seed + 7919 * rank) & 0x7fffffff)
+    idx = np.stack([rs.choice(POOL, size=n_keys, replace=False) for _ in range(n_sets)])      # (n_sets, n_keys)
+    msgs = rs.randint(0, 256, size=(n_sets, MSG_LEN), dtype=np.uint8)
+    msgs[:, 0] = rank
+    msgs[:, 1:5] = np.arange(n_sets, dtype=">u4").view(np.uint8).reshape(n_sets, 4)            # all distinct
+    sk_arr = sks
+    agg = [sum(sk_arr[i] for i in row) % R_ORDER for row in idx]
+    H = eng.hash_to_g2([m.tobytes() for m in msgs])
+    sigs = eng.g2_mul(H.reshape(-1), agg)                        # (n_sets, 192)
+    pks = pool[idx.reshape(-1)]                                  # (n_sets*n_keys, 96)
+    pk_off = np.arange(0, n_sets * n_keys + 1, n_keys, dtype=np.uint32)
+    msg_off = np.arange(0, n_sets * MSG_LEN + 1, MSG_LEN, dtype=np.uint32)
+    return {"sigs": np.ascontiguousarray(sigs.reshape(-1)), "pks": np.ascontiguousarray(pks.reshape(-1)), "pk_off": pk_off,
+            "msgs": np.ascontiguousarray(msgs.reshape(-1)), "msg_off": msg_off, "n": n_sets, "sks": sks, "idx": idx}
+
+
+def draw_scalars(n, seed):
+    import numpy as np
+    from milagro_bls_b200 import SeededRng, draw_scalar
+    rng = SeededRng(seed)
+    return np.array([draw_scalar(rng) for _ in range(n)], dtype=np.uint64)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for k, nme in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- CPU baseline
+def cpu_reference_run(sample_sets, n_keys, seed, threads=None):
+    """Times the CPU restatement of the reference's algorithm (oracle/) on `sample_sets` sets of the same shape,
+    T independent single-threaded instances on disjoint chunks (the reference has no threads).  Returns a dict."""
+    from oracle import cpu_baseline
+    return cpu_baseline.run(sample_sets, n_keys, seed, threads)
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np  # noqa: F401
+    cores = os.cpu_count() or 1
+    sample = max(cores, args.ref_sets)
+    times, last = [], None
+    for it in range(args.warmup + args.steps):
+        last = cpu_reference_run(sample, KEYS_PER_SET, 0xB200 + it, cores)
+        if it >= args.warmup:
+            times.append(last["seconds"])
+    sec = sum(times) / max(len(times), 1)
+    value = sample / sec
+    line = {"impl": "reference", "metric": "verified sig-sets/s (verify_multiple_aggregate_signatures, 128 keys/set)", "value": value,
+            "unit": "sets/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (6x64-bit Montgomery limbs, __int128)",
+            "data": "synthetic",
+            "config": {"workload": f"verify_multiple_aggregate_signatures: {SETS_PER_GPU} sets x {KEYS_PER_SET} keys per GPU (C4/C5)",
+                       "sample_sets_per_step": sample, "keys_per_set": KEYS_PER_SET},
+            "cpu_baseline": {"value": value, "unit": "sets/s", "cores": last["threads"], "kind": last["kind"],
+                             "sample": f"{sample} sets x {KEYS_PER_SET} keys per step, {last['threads']} independent single-threaded instances"},
+            "e2e": {"value": value, "unit": "sets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--sets", type=int, default=SETS_PER_GPU, help="sets per GPU (default: the C4 shape)")
+    ap.add_argument("--keys", type=int, default=KEYS_PER_SET)
+    ap.add_argument("--ref-sets", type=int, default=64, help="sets per step of the CPU reference arm / cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print the per-stage device times to stderr")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_main(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import milagro_bls_b200 as mb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    eng = mb.Engine(local_rank)
+    n, nk = args.sets, args.keys
+    # run every torch op of the benchmark (L2 flush, NCCL all-gather, timing events) on the LIBRARY's stream, so the
+    # CUDA events bracket exactly the stream the kernels are launched on
+    lib_stream = torch.cuda.ExternalStream(int(eng.L.b3_ctx_stream(eng.handle)), device=dev)
+    torch.cuda.set_stream(lib_stream)
+
+    inp = synth_inputs(eng, n, nk, 0xB200, rank)
+    scal = draw_scalars(n, b"bench-%d" % rank)
+    # resident copies
+    d = {k: torch.from_numpy(inp[k]).to(dev) for k in ("sigs", "pks", "pk_off", "msgs", "msg_off")}
+    d["scal"] = torch.from_numpy(scal.view(np.int64)).to(dev)
+    partial = torch.zeros(mb._lib.PARTIAL_BYTES, dtype=torch.uint8, device=dev)
+    gathered = torch.zeros(world * mb._lib.PARTIAL_BYTES, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+    base = rank * n
+
+    stage_acc = {}
+
+    def add_stages():
+        for k, v in eng.stage_ms().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+
+    def step_resident():
+        flush.fill_(1)                                                      # evict L2 between iterations
+        torch.cuda.current_stream().synchronize()
+        eng.verify_multiple_partial_dev(d["sigs"].data_ptr(), d["pks"].data_ptr(), d["pk_off"].data_ptr(), d["msgs"].data_ptr(),
+                                        d["msg_off"].data_ptr(), d["scal"].data_ptr(), n, base, partial.data_ptr())
+        add_stages()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, partial)
+            torch.cuda.current_stream().synchronize()
+            r = eng.combine_partials_dev(gathered.data_ptr(), world)
+        else:
+            r = eng.combine_partials_dev(partial.data_ptr(), 1)
+        add_stages()
+        return r
+
+    # pinned host buffers for the e2e leg
+    pin = {k: torch.from_numpy(inp[k]).pin_memory() for k in ("sigs", "pks", "pk_off", "msgs", "msg_off")}
+    pin["scal"] = torch.from_numpy(scal.view(np.int64)).pin_memory()
+    h2d_bytes = sum(int(t.numel() * t.element_size()) for t in pin.values())
+
+    def step_e2e():
+        flush.fill_(1)
+        torch.cuda.current_stream().synchronize()
+        if world == 1:
+            ok, fb, gt = eng.verify_multiple(pin["sigs"].numpy(), pin["pks"].numpy(), pin["pk_off"].numpy(), pin["msgs"].numpy(),
+                                             pin["msg_off"].numpy(), pin["scal"].numpy().view(np.uint64), want_gt=True)
+            return ok, fb
+        for k in ("sigs", "pks", "pk_off", "msgs", "msg_off", "scal"):
+            d[k].copy_(pin[k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        eng.verify_multiple_partial_dev(d["sigs"].data_ptr(), d["pks"].data_ptr(), d["pk_off"].data_ptr(), d["msgs"].data_ptr(),
+                                        d["msg_off"].data_ptr(), d["scal"].data_ptr(), n, base, partial.data_ptr())
+        dist.all_gather_into_tensor(gathered, partial)
+        torch.cuda.current_stream().synchronize()
+        return eng.combine_partials_dev(gathered.data_ptr(), world)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            r = fn()
+            assert r[0] and r[1] == -1, "verification of the valid synthetic batch must accept"
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = eng.launches
+        t0 = time.perf_counter()
+        e0.record()
+        stage_acc.clear()
+        for _ in range(steps):
+            r = fn()
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)                      # device clock on torch's stream; the library syncs its own stream per call
+        ms = max(ms, 0.0)
+        t = torch.tensor([max(ms, wall * 1e3 if ms == 0 else ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), eng.launches - launches0, {k: v / steps for k, v in dict(stage_acc).items()}, r
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_res, launches, stages, last = timed(step_resident, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps, 1)
+    # correctness inside the bench: a batch with one flipped message bit must reject
+    if rank == 0:
+        bad = d["msgs"].clone()
+        bad[5] ^= 1
+        eng.verify_multiple_partial_dev(d["sigs"].data_ptr(), d["pks"].data_ptr(), d["pk_off"].data_ptr(), bad.data_ptr(),
+                                        d["msg_off"].data_ptr(), d["scal"].data_ptr(), n, base, partial.data_ptr())
+        ok_bad, _ = eng.combine_partials_dev(partial.data_ptr(), 1)
+        assert not ok_bad, "tampered batch must reject"
+
+    total_sets = n * world
+    value = total_sets * args.steps / (ms_res * 1e-3)
+    e2e = total_sets * args.steps / (ms_e2e * 1e-3)
+
+    out = None
+    if rank == 0:
+        peak_mac = eng.imad_peak(wide=True)            # 32x32->64 MACs (IMAD.WIDE pairs) per second, measured live
+        peak_imad = eng.imad_peak(wide=False)
+        dom = max((k for k in stages if k in FP_MULS and FP_MULS[k] > 0), key=lambda k: stages[k])
+        dom_ms = stages[dom]
+        units = n + (1 if dom == "miller_loop" else 0)
+        macs = FP_MULS[dom] * MACS_PER_FP_MUL * units
+        achieved = macs / (dom_ms * 1e-3)
+        whole = FP_MULS_PER_SET * MACS_PER_FP_MUL * n / (sum(stages.values()) * 1e-3)
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            hbm_peak, hbm_src = peaks["hbm_gbs"], "MEASURED_PEAKS.json"
+        except Exception:
+            hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        hbm_achieved = BYTES_PER_SET * n / (sum(stages.values()) * 1e-3) / 1e9
+        roofline = {"bound": "imad", "kernel": dom, "achieved": achieved / 1e9, "peak": peak_mac / 1e9, "unit": "GMAC/s (32x32->64 multiply-accumulate)",
+                    "frac": achieved / peak_mac, "traffic": None,
+                    "kernel_ms": dom_ms, "algorithmic_fp_muls_per_unit": FP_MULS[dom], "macs_per_fp_mul": MACS_PER_FP_MUL, "units_per_launch": units,
+                    "peak_source": "live probe b3_imad_peak(wide=1): IMAD.WIDE carry chains, all SMs",
+                    "plain_imad_peak_gops": peak_imad / 1e9,
+                    "whole_step": {"achieved": whole / 1e9, "frac": whole / peak_mac, "fp_muls_per_set": FP_MULS_PER_SET},
+                    "hbm": {"achieved_gbs": hbm_achieved, "peak_gbs": hbm_peak, "frac": hbm_achieved / hbm_peak, "peak_source": hbm_src,
+                            "algorithmic_bytes_per_set": BYTES_PER_SET},
+                    "stage_ms": stages}
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                c = cpu_reference_run(max(os.cpu_count() or 1, args.ref_sets), nk, 0xB200, os.cpu_count() or 1)
+                cpu = {"value": c["sets"] / c["seconds"], "unit": "sets/s", "cores": c["threads"], "kind": c["kind"],
+                       "sample": f"{c['sets']} sets x {nk} keys, {c['threads']} independent single-threaded instances, {c['seconds']:.1f} s"}
+            except Exception as ex:                                        # noqa: BLE001
+                cpu = {"value": None, "unit": "sets/s", "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
+        out = {"metric": "verified sig-sets/s (verify_multiple_aggregate_signatures, 128 keys/set)", "value": value, "unit": "sets/s",
+               "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_res / args.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (12x32-bit Montgomery limbs, IMAD.WIDE)",
+               "data": "synthetic",
+               "config": {"workload": f"verify_multiple_aggregate_signatures: {n} sets x {nk} keys per GPU "
+                                      f"({'C4' if world == 1 else 'C5-style'}: {total_sets} sets total), 32-byte distinct messages, 63-bit scalars",
+                          "sets_per_gpu": n, "keys_per_set": nk, "total_sets": total_sets, "parallelism": f"set-sharded x{world}",
+                          "cache": "L2 flushed (256 MiB write) before every step; inputs ~103 MB per GPU"},
+               "e2e": {"value": e2e, "unit": "sets/s", "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": (576 + 16) * world,
+                       "ms_per_step": ms_e2e / args.steps},
+               "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+               "accept": bool(last[0])}
+        if args.breakdown:
+            print(json.dumps(stages, indent=1), file=sys.stderr)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -51,6 +51,11 @@ void* b3_ctx_stream(b3_ctx* ctx);
 uint64_t b3_ctx_launch_count(b3_ctx* ctx);
 /* device time in ms of the most recent call's kernels, and of its dominant (Miller-loop) kernel */
 float b3_ctx_last_kernel_ms(b3_ctx* ctx, int which);
+/* per-stage device time (ms, CUDA events on the context's stream) of the most recent verification / hash call;
+ * stages 0 .. b3_stage_count()-1 are named by b3_stage_name() */
+float b3_ctx_stage_ms(b3_ctx* ctx, int stage);
+const char* b3_stage_name(int stage);
+int b3_stage_count(void);
 
 /* ---- (de)serialisation: PublicKey::{from_bytes, from_bytes_unchecked, as_bytes} (M/src/keys.rs:140-160),
  *      Signature::{from_bytes, as_bytes} (M/src/signature.rs:43-51), AggregateSignature::{from_bytes, as_bytes}

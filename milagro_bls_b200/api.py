@@ -92,6 +92,10 @@ class Engine:
     def last_kernel_ms(self, which=0):
         return float(self.L.b3_ctx_last_kernel_ms(self.handle, which))
 
+    def stage_ms(self):
+        """{stage name: device ms} of the most recent verification / hash call (CUDA events on the library's stream)."""
+        return {self.L.b3_stage_name(i).decode(): float(self.L.b3_ctx_stage_ms(self.handle, i)) for i in range(self.L.b3_stage_count())}
+
     def g1_decompress(self, data48, validate=True):
         n = len(data48) // 48
         p, keep = _buf(data48)

@@ -17,6 +17,13 @@
 static const uint8_t kDstG2[] = "BLS_SIG_BLS12381G2_XMD:SHA-256_SSWU_RO_POP_";   // A/bls381/proof_of_possession.rs:38
 static const size_t kDstG2Len = 43;
 
+#define B3_MAX_MARKS 24
+#define B3_N_STAGES 10
+// stage ids (b3_ctx_stage_ms / b3_stage_name)
+enum { ST_SIG_CHECK = 0, ST_AGGREGATE, ST_G1_MUL, ST_HASH_TO_G2, ST_G2_MUL_SUM, ST_MILLER, ST_FP12_PRODUCT, ST_FINAL_EXP, ST_COPY, ST_END };
+static const char* kStageNames[B3_N_STAGES] = {"g2_parse_subgroup_check", "g1_aggregate", "g1_scalar_mul_affine", "hash_to_g2_affine",
+                                               "g2_scalar_mul_sum", "miller_loop", "fp12_product_tree", "final_exp", "copies", "end"};
+
 struct dev_buf {
     void* p = nullptr;
     size_t cap = 0;
@@ -29,6 +36,11 @@ struct b3_ctx {
     uint64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // 0/1: whole call, 2/3: Miller kernel
     float last_ms[2] = {0.f, 0.f};
+    // stage marks of the most recent verification call: mark i opens stage mark_id[i]; the last mark closes the call
+    cudaEvent_t mark_ev[B3_MAX_MARKS];
+    int mark_id[B3_MAX_MARKS];
+    int n_marks = 0;
+    float stage_ms[B3_N_STAGES];
     // scratch (grown on demand, reused across calls)
     dev_buf in_a, in_b, in_c, in_d, in_e, in_f;      // staged host inputs
     dev_buf g1j, g1j2, g1a, g2a_sig, g2j, g2j2, g2a, f12a, f12b, status, ok, misc, outb;
@@ -79,6 +91,8 @@ extern "C" int b3_ctx_create(int device, b3_ctx** out) {
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B3_ERR_CUDA; }
     for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
+    for (int i = 0; i < B3_MAX_MARKS; i++) cudaEventCreate(&ctx->mark_ev[i]);
+    for (int i = 0; i < B3_N_STAGES; i++) ctx->stage_ms[i] = 0.f;
     if (cudaMalloc((void**)&ctx->d_dst, 256) != cudaSuccess) { delete ctx; return B3_ERR_CUDA; }
     cudaMemcpy(ctx->d_dst, kDstG2, kDstG2Len, cudaMemcpyHostToDevice);
     *out = ctx;
@@ -94,6 +108,7 @@ extern "C" void b3_ctx_destroy(b3_ctx* ctx) {
     for (dev_buf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_dst) cudaFree(ctx->d_dst);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < B3_MAX_MARKS; i++) cudaEventDestroy(ctx->mark_ev[i]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -101,6 +116,24 @@ extern "C" const char* b3_last_error(b3_ctx* ctx) { return ctx ? ctx->err.c_str(
 extern "C" void* b3_ctx_stream(b3_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" uint64_t b3_ctx_launch_count(b3_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" float b3_ctx_last_kernel_ms(b3_ctx* ctx, int which) { return (ctx && which >= 0 && which < 2) ? ctx->last_ms[which] : 0.f; }
+extern "C" float b3_ctx_stage_ms(b3_ctx* ctx, int stage) { return (ctx && stage >= 0 && stage < B3_N_STAGES) ? ctx->stage_ms[stage] : 0.f; }
+extern "C" const char* b3_stage_name(int stage) { return (stage >= 0 && stage < B3_N_STAGES) ? kStageNames[stage] : ""; }
+extern "C" int b3_stage_count(void) { return B3_N_STAGES - 1; }
+static void mark_reset(b3_ctx* ctx) { ctx->n_marks = 0; }
+static void mark(b3_ctx* ctx, int id) {
+    if (ctx->n_marks >= B3_MAX_MARKS) return;
+    cudaEventRecord(ctx->mark_ev[ctx->n_marks], ctx->stream);
+    ctx->mark_id[ctx->n_marks++] = id;
+}
+// after a stream synchronize: fold the marks into per-stage durations
+static void mark_collect(b3_ctx* ctx) {
+    for (int i = 0; i < B3_N_STAGES; i++) ctx->stage_ms[i] = 0.f;
+    for (int i = 0; i + 1 < ctx->n_marks; i++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->mark_ev[i], ctx->mark_ev[i + 1]) == cudaSuccess) ctx->stage_ms[ctx->mark_id[i]] += ms;
+    }
+    cudaGetLastError();
+}
 
 static int h2d(b3_ctx* ctx, dev_buf& b, const void* src, size_t bytes) {
     CKR(ensure(ctx, b, bytes ? bytes : 1));
@@ -157,8 +190,10 @@ static int miller_product(b3_ctx* ctx, const g2_aff* q, const g1_aff* p, size_t 
         return B3_OK;
     }
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    mark(ctx, ST_MILLER);
     LAUNCH(k_miller, nblk(n_pairs), B3_TPB, q, p, n_pairs, fa);
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    mark(ctx, ST_FP12_PRODUCT);
     return fp12_product(ctx, fa, (fp12*)ctx->f12b.p, n_pairs, res);
 }
 // final exponentiation of *m -> accept / gt on the host
@@ -166,7 +201,9 @@ static int finish(b3_ctx* ctx, const fp12* m, int* accept, uint8_t* gt576) {
     CKR(ensure(ctx, ctx->outb, 576 + 16));
     uint8_t* d_gt = (uint8_t*)ctx->outb.p;
     int32_t* d_one = (int32_t*)(d_gt + 576);
+    mark(ctx, ST_FINAL_EXP);
     LAUNCH(k_final_exp, 1, 1, m, d_gt, d_one);
+    mark(ctx, ST_END);
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     int32_t one = 0;
     uint8_t gt[576];
@@ -176,6 +213,7 @@ static int finish(b3_ctx* ctx, const fp12* m, int* accept, uint8_t* gt576) {
     cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev[0], ctx->ev[1]);
     if (cudaEventElapsedTime(&ctx->last_ms[1], ctx->ev[2], ctx->ev[3]) != cudaSuccess) ctx->last_ms[1] = 0.f;
     cudaGetLastError();
+    mark_collect(ctx);
     if (gt576) memcpy(gt576, gt, 576);
     if (accept) *accept = one ? 1 : 0;
     return B3_OK;
@@ -350,10 +388,15 @@ extern "C" int b3_hash_to_g2_dev(b3_ctx* ctx, const uint8_t* msgs_dev, const uin
     if (n == 0) return B3_OK;
     CKR(ensure(ctx, ctx->g2a, sizeof(g2_aff) * n));
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    mark_reset(ctx);
+    mark(ctx, ST_HASH_TO_G2);
     CKR(hash_to_g2_affine_dev(ctx, msgs_dev, off_dev, n, ctx->d_dst, (uint32_t)kDstG2Len, (g2_aff*)ctx->g2a.p));
+    mark(ctx, ST_COPY);
     LAUNCH(k_g2_aff_to_wire, nblk(n), B3_TPB, (const g2_aff*)ctx->g2a.p, n, out192_dev);
+    mark(ctx, ST_END);
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     CKR(sync(ctx));
+    mark_collect(ctx);
     cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev[0], ctx->ev[1]);
     return B3_OK;
 }
@@ -421,6 +464,7 @@ extern "C" int b3_fast_aggregate_verify(b3_ctx* ctx, const uint8_t sig192[192], 
     if (!sig192 || (!msg && msg_len)) return B3_ERR_ARG;
     if (n_pks == 0) return B3_OK;                       // M/src/aggregates.rs:179-181
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    mark_reset(ctx);
     CKR(parse_sig(ctx, sig192));
     uint32_t off[2] = {0, (uint32_t)n_pks};
     CKR(h2d(ctx, ctx->in_b, pks96, 96 * n_pks));
@@ -437,6 +481,7 @@ static int verify_single_key(b3_ctx* ctx, const uint8_t* sig192, const uint8_t* 
     if (accept) *accept = 0;
     if (!sig192 || !pk96 || (!msg && msg_len)) return B3_ERR_ARG;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    mark_reset(ctx);
     CKR(parse_sig(ctx, sig192));
     CKR(h2d(ctx, ctx->in_b, pk96, 96));
     CKR(ensure(ctx, ctx->g1j, sizeof(g1_jac) * 2));
@@ -461,6 +506,7 @@ extern "C" int b3_aggregate_verify(b3_ctx* ctx, const uint8_t sig192[192], const
     if (n == 0) return B3_OK;                            // M/src/aggregates.rs:132-134
     if (!sig192 || !pks96 || !msg_off) return B3_ERR_ARG;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    mark_reset(ctx);
     CKR(parse_sig(ctx, sig192));
     CKR(h2d(ctx, ctx->in_b, pks96, 96 * n));
     CKR(h2d(ctx, ctx->in_c, msgs, msg_off[n]));
@@ -511,17 +557,22 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
     g1_aff* p = (g1_aff*)ctx->g1a.p;
     if (n > 0) {
         // 1. signatures: parse + on-curve + subgroup check (M/src/aggregates.rs:274-276)
+        mark(ctx, ST_SIG_CHECK);
         LAUNCH(k_g2_parse, nblk(n), B3_TPB, d_sigs, n, (g2_aff*)ctx->g2a_sig.p, d_st_sig, (int32_t*)ctx->ok.p, 1, 1);
         LAUNCH(k_first_bad, nblk(n), B3_TPB, (const int32_t*)ctx->ok.p, n, index_base, d_first_bad);
         // 2. aggregate public keys
+        mark(ctx, ST_AGGREGATE);
         if (d_pk_off) CKR(g1_aggregate_dev_impl(ctx, d_pks, d_pk_off, n, total_keys, (g1_jac*)ctx->g1j.p, d_st_key));
         else LAUNCH(k_g1_parse, nblk(n), B3_TPB, d_pks, n, (g1_jac*)ctx->g1j.p, d_st_key, 1);
         // 3. P_j = [c_j] apk_j  (M/src/aggregates.rs:293), affine
+        mark(ctx, ST_G1_MUL);
         LAUNCH(k_g1_mul_u64, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j.p, d_scalars, n, (g1_jac*)ctx->g1j2.p);
         LAUNCH(k_g1_to_affine, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j2.p, n, p);
         // 4. H_j = hash_to_curve_g2(msg_j), affine (M/src/aggregates.rs:290,296)
+        mark(ctx, ST_HASH_TO_G2);
         CKR(hash_to_g2_affine_dev(ctx, d_msgs, d_msg_off, n, ctx->d_dst, (uint32_t)kDstG2Len, q));
         // 5. S = sum_j [c_j] sig_j (M/src/aggregates.rs:303)
+        mark(ctx, ST_G2_MUL_SUM);
         CKR(ensure(ctx, ctx->g2j, sizeof(g2_jac) * (n + 1)));
         LAUNCH(k_g2_mul_u64, nblk(n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, d_scalars, n, (g2_jac*)ctx->g2j.p);
         g2_jac* s;
@@ -553,6 +604,7 @@ extern "C" int b3_verify_multiple(b3_ctx* ctx, const uint8_t* sigs192, const uin
     if (first_bad) *first_bad = -1;
     if (n && (!sigs192 || !pks96 || !msg_off || !scalars)) return B3_ERR_ARG;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    mark_reset(ctx);
     size_t total_keys = pk_off ? pk_off[n] : n;
     if (n) {
         CKR(h2d(ctx, ctx->in_a, sigs192, 192 * n));
@@ -605,6 +657,7 @@ extern "C" int b3_verify_multiple_partial_dev(b3_ctx* ctx, const uint8_t* sigs19
     CKR(begin(ctx));
     if (!partial_dev) return B3_ERR_ARG;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    mark_reset(ctx);
     size_t total_keys = n;
     if (pk_off_dev && n) {
         uint32_t t = 0;
@@ -619,8 +672,10 @@ extern "C" int b3_verify_multiple_partial_dev(b3_ctx* ctx, const uint8_t* sigs19
                              &perr));
     if (perr) return perr;
     LAUNCH(k_pack_partial, 1, 1, (const fp12*)res, (const long long*)d_fb, (partial_rec*)partial_dev);
+    mark(ctx, ST_END);
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     CKR(sync(ctx));
+    mark_collect(ctx);
     cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev[0], ctx->ev[1]);
     if (cudaEventElapsedTime(&ctx->last_ms[1], ctx->ev[2], ctx->ev[3]) != cudaSuccess) ctx->last_ms[1] = 0.f;
     cudaGetLastError();
@@ -633,6 +688,7 @@ extern "C" int b3_combine_partials_dev(b3_ctx* ctx, const uint8_t* partials_dev,
     if (first_bad) *first_bad = -1;
     if (!partials_dev || n_partials == 0) return B3_ERR_ARG;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    mark_reset(ctx);
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     CKR(ensure(ctx, ctx->f12a, sizeof(fp12) * (n_partials + 1)));
@@ -689,6 +745,7 @@ extern "C" int b3_imad_peak(b3_ctx* ctx, int wide, double* ops_per_s) {
     double best = 0;
     for (int rep = 0; rep < 5; rep++) {
         CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    mark_reset(ctx);
         if (wide) LAUNCH(k_imad_wide_peak, blocks, threads, (uint32_t*)ctx->outb.p, iters, 12345u + rep);
         else LAUNCH(k_imad_peak, blocks, threads, (uint32_t*)ctx->outb.p, iters, 12345u + rep);
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));
