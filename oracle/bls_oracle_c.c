@@ -1,0 +1,678 @@
+/* CPU oracle in C -- TEST INFRASTRUCTURE ONLY (checker at large sizes + the CPU baseline bench.py reports).
+ *
+ * A restatement of the reference's ALGORITHM CHOICES for the verification path (the Rust crate itself cannot be
+ * built here: no rustc/cargo).  A = /root/reference/incubator-milagro-crypto-rust/src, M = /root/reference/src.
+ *   - Fp: Montgomery residues with 128-bit accumulators (A/big.rs:950-1106, A/fp.rs:306-314).  Limbs here are
+ *     6 x 64-bit (R = 2^384) instead of the reference's 7 x 58-bit with lazy-reduction excess counters; this is
+ *     at least as fast per multiplication, so the baseline is not slower than the reference's own field layer.
+ *   - Fp2 / Fp4 / Fp12 tower of A/fp2.rs, A/fp4.rs, A/fp12.rs (2-2-3), sparse line products.
+ *   - complete projective point formulas (A/ecp.rs:552-592,743-819, A/ecp2.rs:368-527): oracle/ec_generic.inc.
+ *   - GLV / GS scalar paths with full-length joint ladders, incl. the [r]P subgroup checks
+ *     (A/pair.rs:546-693, A/bls381/core.rs:116-127).
+ *   - per-bit-accumulator multi-pairing initmp/another/miller (A/pair.rs:156-238) and the BLS final
+ *     exponentiation (A/pair.rs:409-541), Fermat inversions (A/fp.rs:608-616).
+ *   - non-constant-time SSWU with the FP2::sqrt flow incl. Jacobi symbols (A/hash_to_curve.rs:283-346,
+ *     A/fp2.rs:304-339), 3-isogeny (A/bls381/iso.rs:177-206), Budroni-Pintore cofactor clearing
+ *     (A/ecp2.rs:784-805).
+ *   - API semantics of M/src/aggregates.rs:29-56,130-316 and M/src/signature.rs:27-40.
+ * Parity: pinned against the reference's hash-to-curve vectors and checked bit-for-bit against
+ * oracle/bls_oracle.py (tests/test_oracle_c.py); GT values unpinned by the reference (see bls_oracle.py).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef unsigned __int128 u128;
+typedef struct { uint64_t l[6]; } fp_t;
+typedef struct { fp_t a, b; } fp2_t;              /* a + i b */
+typedef struct { fp2_t a, b; } fp4_t;             /* a + j b, j^2 = 1+i */
+typedef struct { fp4_t a, b, c; } fp12_t;         /* a + b w + c w^2, w^3 = j */
+
+#include "bls_oracle_consts.h"
+
+/* ------------------------------------------------------------------------------------------------ Fp */
+static int fp_is_zero(const fp_t *a) { return (a->l[0] | a->l[1] | a->l[2] | a->l[3] | a->l[4] | a->l[5]) == 0; }
+static int fp_eq(const fp_t *a, const fp_t *b) { return memcmp(a, b, sizeof(fp_t)) == 0; }
+static int raw_geq(const uint64_t *a, const uint64_t *b) {
+    for (int i = 5; i >= 0; i--) { if (a[i] > b[i]) return 1; if (a[i] < b[i]) return 0; }
+    return 1;
+}
+static void raw_sub(uint64_t *r, const uint64_t *a, const uint64_t *b) {
+    u128 br = 0;
+    for (int i = 0; i < 6; i++) { u128 t = (u128)a[i] - b[i] - br; r[i] = (uint64_t)t; br = (t >> 64) & 1; }
+}
+static void fp_add(fp_t *r, const fp_t *a, const fp_t *b) {
+    u128 c = 0; uint64_t t[6];
+    for (int i = 0; i < 6; i++) { c += (u128)a->l[i] + b->l[i]; t[i] = (uint64_t)c; c >>= 64; }
+    if (raw_geq(t, FP_P.l)) raw_sub(r->l, t, FP_P.l); else memcpy(r->l, t, 48);
+}
+static void fp_sub(fp_t *r, const fp_t *a, const fp_t *b) {
+    if (raw_geq(a->l, b->l)) raw_sub(r->l, a->l, b->l);
+    else { uint64_t t[6]; raw_sub(t, b->l, a->l); raw_sub(r->l, FP_P.l, t); }
+}
+static void fp_neg(fp_t *r, const fp_t *a) { if (fp_is_zero(a)) *r = *a; else raw_sub(r->l, FP_P.l, a->l); }
+/* CIOS Montgomery product */
+static void fp_mul(fp_t *r, const fp_t *a, const fp_t *b) {
+    uint64_t t[8] = {0};
+    for (int i = 0; i < 6; i++) {
+        u128 c = 0;
+        for (int j = 0; j < 6; j++) { c += (u128)a->l[j] * b->l[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+        c += t[6]; t[6] = (uint64_t)c; t[7] = (uint64_t)(c >> 64);
+        uint64_t m = t[0] * FP_PINV;
+        c = (u128)m * FP_P.l[0] + t[0]; c >>= 64;
+        for (int j = 1; j < 6; j++) { c += (u128)m * FP_P.l[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+        c += t[6]; t[5] = (uint64_t)c; t[6] = t[7] + (uint64_t)(c >> 64);
+    }
+    if (t[6] || raw_geq(t, FP_P.l)) raw_sub(r->l, t, FP_P.l); else memcpy(r->l, t, 48);
+}
+static void fp_sqr(fp_t *r, const fp_t *a) { fp_mul(r, a, a); }
+static void fp_pow(fp_t *r, const fp_t *a, const fp_t *e) {       /* A/fp.rs:635-686 (plain binary ladder here) */
+    fp_t acc = FP_ONE; int started = 0;
+    for (int i = 383; i >= 0; i--) {
+        if (started) fp_sqr(&acc, &acc);
+        if ((e->l[i >> 6] >> (i & 63)) & 1) { if (started) fp_mul(&acc, &acc, a); else { acc = *a; started = 1; } }
+    }
+    *r = acc;
+}
+static void fp_inv(fp_t *r, const fp_t *a) { fp_pow(r, a, &EXP_PM2); }          /* A/fp.rs:608-616 */
+static void fp_sqrt(fp_t *r, const fp_t *a) { fp_pow(r, a, &EXP_SQRT); }        /* A/fp.rs:717-729 */
+static void fp_from_mont(fp_t *r, const fp_t *a) { fp_t one = {{1, 0, 0, 0, 0, 0}}; fp_mul(r, a, &one); }
+static void fp_to_mont(fp_t *r, const fp_t *a) { fp_mul(r, a, &FP_R2); }
+static void fp_half(fp_t *r, const fp_t *a) { fp_mul(r, a, &FP_HALF); }
+/* Jacobi symbol of the canonical value by the binary algorithm (A/big.rs:850-886 via A/fp.rs:733-737) */
+static int raw_is_zero(const uint64_t *a) { return (a[0] | a[1] | a[2] | a[3] | a[4] | a[5]) == 0; }
+static void raw_shr1(uint64_t *a) { for (int i = 0; i < 5; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 63); a[5] >>= 1; }
+static int fp_jacobi(const fp_t *am) {
+    fp_t c; fp_from_mont(&c, am);
+    uint64_t a[6], n[6]; memcpy(a, c.l, 48); memcpy(n, FP_P.l, 48);
+    if (raw_is_zero(a)) return 0;
+    int t = 1;
+    while (!raw_is_zero(a)) {
+        while (!(a[0] & 1)) { raw_shr1(a); uint64_t m8 = n[0] & 7; if (m8 == 3 || m8 == 5) t = -t; }
+        if (!raw_geq(a, n) ) { uint64_t tmp[6]; memcpy(tmp, a, 48); memcpy(a, n, 48); memcpy(n, tmp, 48);
+                               if ((a[0] & 3) == 3 && (n[0] & 3) == 3) t = -t; }
+        raw_sub(a, a, n); raw_shr1(a);
+        { uint64_t m8 = n[0] & 7; if (m8 == 3 || m8 == 5) t = -t; }
+    }
+    return (n[0] == 1 && !(n[1] | n[2] | n[3] | n[4] | n[5])) ? t : 0;
+}
+static void fp_from_be(fp_t *r, const uint8_t *b) {               /* canonical bytes -> Montgomery */
+    fp_t t;
+    for (int i = 0; i < 6; i++) { uint64_t v = 0; for (int k = 0; k < 8; k++) v = (v << 8) | b[40 - 8 * i + k]; t.l[i] = v; }
+    fp_to_mont(r, &t);
+}
+static int be_lt_p(const uint8_t *b) {
+    uint64_t t[6];
+    for (int i = 0; i < 6; i++) { uint64_t v = 0; for (int k = 0; k < 8; k++) v = (v << 8) | b[40 - 8 * i + k]; t[i] = v; }
+    return !raw_geq(t, FP_P.l);
+}
+static void fp_to_be(uint8_t *b, const fp_t *a) {
+    fp_t t; fp_from_mont(&t, a);
+    for (int i = 0; i < 6; i++) for (int k = 0; k < 8; k++) b[40 - 8 * i + k] = (uint8_t)(t.l[i] >> (56 - 8 * k));
+}
+static int fp_parity(const fp_t *a) { fp_t t; fp_from_mont(&t, a); return (int)(t.l[0] & 1); }
+static void fp_set_u64(fp_t *r, uint64_t v) { fp_t t = {{v, 0, 0, 0, 0, 0}}; fp_to_mont(r, &t); }
+
+/* ------------------------------------------------------------------------------------------------ Fp2 */
+static void f2_add(fp2_t *r, const fp2_t *a, const fp2_t *b) { fp_add(&r->a, &a->a, &b->a); fp_add(&r->b, &a->b, &b->b); }
+static void f2_sub(fp2_t *r, const fp2_t *a, const fp2_t *b) { fp_sub(&r->a, &a->a, &b->a); fp_sub(&r->b, &a->b, &b->b); }
+static void f2_neg(fp2_t *r, const fp2_t *a) { fp_neg(&r->a, &a->a); fp_neg(&r->b, &a->b); }
+static void f2_conj(fp2_t *r, const fp2_t *a) { r->a = a->a; fp_neg(&r->b, &a->b); }
+static int f2_is_zero(const fp2_t *a) { return fp_is_zero(&a->a) && fp_is_zero(&a->b); }
+static int f2_eq(const fp2_t *a, const fp2_t *b) { return fp_eq(&a->a, &b->a) && fp_eq(&a->b, &b->b); }
+static void f2_zero(fp2_t *r) { memset(r, 0, sizeof(*r)); }
+static void f2_one(fp2_t *r) { r->a = FP_ONE; memset(&r->b, 0, sizeof(fp_t)); }
+static void f2_mul(fp2_t *r, const fp2_t *x, const fp2_t *y) {                  /* A/fp2.rs:258-300 */
+    fp_t t0, t1, s0, s1;
+    fp_add(&s0, &x->a, &x->b); fp_add(&s1, &y->a, &y->b);
+    fp_mul(&t0, &x->a, &y->a); fp_mul(&t1, &x->b, &y->b); fp_mul(&s0, &s0, &s1);
+    fp_sub(&s0, &s0, &t0); fp_sub(&r->b, &s0, &t1); fp_sub(&r->a, &t0, &t1);
+}
+static void f2_sqr(fp2_t *r, const fp2_t *x) {                                    /* A/fp2.rs:237-255 */
+    fp_t s, d, m;
+    fp_add(&s, &x->a, &x->b); fp_sub(&d, &x->a, &x->b); fp_mul(&m, &x->a, &x->b);
+    fp_mul(&r->a, &s, &d); fp_add(&r->b, &m, &m);
+}
+static void f2_pmul(fp2_t *r, const fp2_t *x, const fp_t *s) { fp_mul(&r->a, &x->a, s); fp_mul(&r->b, &x->b, s); }
+static void f2_imul(fp2_t *r, const fp2_t *x, int k) {                            /* small-constant multiple by additions */
+    fp2_t acc; f2_zero(&acc); fp2_t base = *x;
+    while (k) { if (k & 1) f2_add(&acc, &acc, &base); f2_add(&base, &base, &base); k >>= 1; }
+    *r = acc;
+}
+static void f2_mul_ip(fp2_t *r, const fp2_t *x) {                                 /* *(1+i), A/fp2.rs:401-408 */
+    fp_t t; fp_sub(&t, &x->a, &x->b); fp_add(&r->b, &x->a, &x->b); r->a = t;
+}
+static void f2_inv(fp2_t *r, const fp2_t *x) {                                    /* A/fp2.rs:370-383 */
+    fp_t n, t; fp_sqr(&n, &x->a); fp_sqr(&t, &x->b); fp_add(&n, &n, &t); fp_inv(&n, &n);
+    fp_mul(&r->a, &x->a, &n); fp_mul(&t, &x->b, &n); fp_neg(&r->b, &t);
+}
+static int f2_sqrt(fp2_t *x) {                                                    /* A/fp2.rs:304-339 */
+    if (f2_is_zero(x)) return 1;
+    fp_t w1, w2;
+    fp_sqr(&w1, &x->b); fp_sqr(&w2, &x->a); fp_add(&w1, &w1, &w2);
+    if (fp_jacobi(&w1) != 1) { f2_zero(x); return 0; }
+    fp_sqrt(&w2, &w1); w1 = w2;
+    fp_add(&w2, &x->a, &w1); fp_half(&w2, &w2);
+    if (fp_jacobi(&w2) != 1) {
+        fp_sub(&w2, &x->a, &w1); fp_half(&w2, &w2);
+        if (fp_jacobi(&w2) != 1) { f2_zero(x); return 0; }
+    }
+    fp_sqrt(&w1, &w2);
+    x->a = w1;
+    fp_add(&w1, &w1, &w1); fp_inv(&w1, &w1);
+    fp_mul(&x->b, &x->b, &w1);
+    return 1;
+}
+static int f2_sgn0(const fp2_t *x) { return fp_is_zero(&x->a) ? fp_parity(&x->b) : fp_parity(&x->a); }   /* A/fp2.rs:449-455 */
+
+/* ------------------------------------------------------------------------------------------------ Fp4 */
+static void f4_add(fp4_t *r, const fp4_t *x, const fp4_t *y) { f2_add(&r->a, &x->a, &y->a); f2_add(&r->b, &x->b, &y->b); }
+static void f4_sub(fp4_t *r, const fp4_t *x, const fp4_t *y) { f2_sub(&r->a, &x->a, &y->a); f2_sub(&r->b, &x->b, &y->b); }
+static void f4_neg(fp4_t *r, const fp4_t *x) { f2_neg(&r->a, &x->a); f2_neg(&r->b, &x->b); }
+static void f4_conj(fp4_t *r, const fp4_t *x) { r->a = x->a; f2_neg(&r->b, &x->b); }
+static void f4_zero(fp4_t *r) { memset(r, 0, sizeof(*r)); }
+static void f4_mul(fp4_t *r, const fp4_t *x, const fp4_t *y) {                    /* A/fp4.rs:275-308 */
+    fp2_t t0, t1, t2, s;
+    f2_mul(&t0, &x->a, &y->a); f2_mul(&t1, &x->b, &y->b);
+    f2_add(&t2, &x->a, &x->b); f2_add(&s, &y->a, &y->b); f2_mul(&t2, &t2, &s);
+    f2_sub(&t2, &t2, &t0); f2_sub(&r->b, &t2, &t1);
+    f2_mul_ip(&t1, &t1); f2_add(&r->a, &t0, &t1);
+}
+static void f4_sqr(fp4_t *r, const fp4_t *x) {                                     /* A/fp4.rs:243-272 */
+    fp2_t t1, t2, t3;
+    f2_mul(&t3, &x->a, &x->b);                       /* ab */
+    f2_mul_ip(&t2, &x->b);                           /* (1+i) b */
+    f2_add(&t1, &x->a, &x->b); f2_add(&t2, &x->a, &t2);
+    f2_mul(&t1, &t1, &t2);                           /* (a+b)(a+(1+i)b) */
+    f2_mul_ip(&t2, &t3);
+    f2_sub(&t1, &t1, &t3); f2_sub(&r->a, &t1, &t2);
+    f2_add(&r->b, &t3, &t3);
+}
+static void f4_times_i(fp4_t *r, const fp4_t *x) { fp2_t t; f2_mul_ip(&t, &x->b); r->b = x->a; r->a = t; }   /* A/fp4.rs:359-367 */
+static void f4_pmul(fp4_t *r, const fp4_t *x, const fp2_t *s) { f2_mul(&r->a, &x->a, s); f2_mul(&r->b, &x->b, s); }
+static void f4_inv(fp4_t *r, const fp4_t *x) {                                     /* A/fp4.rs:340-356 */
+    fp2_t t1, t2;
+    f2_sqr(&t1, &x->a); f2_sqr(&t2, &x->b); f2_mul_ip(&t2, &t2); f2_sub(&t1, &t1, &t2); f2_inv(&t1, &t1);
+    f2_mul(&r->a, &x->a, &t1); f2_mul(&t2, &x->b, &t1); f2_neg(&r->b, &t2);
+}
+static void f4_frob(fp4_t *r, const fp4_t *x, const fp2_t *f3) { f2_conj(&r->a, &x->a); fp2_t t; f2_conj(&t, &x->b); f2_mul(&r->b, &t, f3); }
+
+/* ------------------------------------------------------------------------------------------------ Fp12 */
+static void f12_one(fp12_t *r) { memset(r, 0, sizeof(*r)); r->a.a.a = FP_ONE; }
+static int f12_is_one(const fp12_t *x) { fp12_t o; f12_one(&o); return memcmp(x, &o, sizeof(o)) == 0; }
+static void f12_mul(fp12_t *r, const fp12_t *x, const fp12_t *y) {                /* A/fp12.rs:300-366 (Karatsuba) */
+    fp4_t z0, z1, z2, z3, t0, t1;
+    f4_mul(&z0, &x->a, &y->a);
+    f4_mul(&z2, &x->b, &y->b);
+    f4_add(&t0, &x->a, &x->b); f4_add(&t1, &y->a, &y->b); f4_mul(&z1, &t0, &t1);
+    f4_add(&t0, &x->b, &x->c); f4_add(&t1, &y->b, &y->c); f4_mul(&z3, &t0, &t1);
+    f4_sub(&z1, &z1, &z0); f4_sub(&z1, &z1, &z2);                     /* ab' + a'b */
+    f4_sub(&z3, &z3, &z2);                                             /* bc' + b'c + cc' */
+    fp4_t ac, cc;
+    f4_add(&t0, &x->a, &x->c); f4_add(&t1, &y->a, &y->c); f4_mul(&ac, &t0, &t1);
+    f4_mul(&cc, &x->c, &y->c);
+    f4_sub(&ac, &ac, &z0); f4_sub(&ac, &ac, &cc);                      /* ac' + a'c */
+    f4_sub(&z3, &z3, &cc);                                             /* bc' + b'c */
+    f4_times_i(&z3, &z3); f4_add(&r->a, &z0, &z3);
+    f4_times_i(&t0, &cc); f4_add(&r->b, &z1, &t0);
+    f4_add(&r->c, &ac, &z2);
+}
+static void f12_sqr(fp12_t *r, const fp12_t *x) {                                  /* A/fp12.rs:252-297 (Chung-Hasan SQR2) */
+    fp4_t A, B, C, D, t;
+    f4_sqr(&A, &x->a);
+    f4_mul(&B, &x->b, &x->c); f4_add(&B, &B, &B);
+    f4_sqr(&C, &x->c);
+    f4_mul(&D, &x->a, &x->b); f4_add(&D, &D, &D);
+    f4_add(&t, &x->a, &x->b); f4_add(&t, &t, &x->c); f4_sqr(&t, &t);
+    f4_times_i(&r->a, &B); f4_add(&r->a, &r->a, &A);
+    fp4_t ci; f4_times_i(&ci, &C); f4_add(&r->b, &ci, &D);
+    f4_sub(&t, &t, &A); f4_sub(&t, &t, &B); f4_sub(&t, &t, &C); f4_sub(&r->c, &t, &D);
+}
+static void f12_conj(fp12_t *r, const fp12_t *x) { f4_conj(&r->a, &x->a); fp4_t t; f4_conj(&t, &x->b); f4_neg(&r->b, &t); f4_conj(&r->c, &x->c); }
+static void f12_inv(fp12_t *r, const fp12_t *x) {                                  /* A/fp12.rs:710-754 */
+    fp4_t f0, f1, f2, f3, t;
+    f4_sqr(&f0, &x->a); f4_mul(&t, &x->b, &x->c); f4_times_i(&t, &t); f4_sub(&f0, &f0, &t);
+    f4_sqr(&f1, &x->c); f4_times_i(&f1, &f1); f4_mul(&t, &x->a, &x->b); f4_sub(&f1, &f1, &t);
+    f4_sqr(&f2, &x->b); f4_mul(&t, &x->a, &x->c); f4_sub(&f2, &f2, &t);
+    f4_mul(&f3, &x->b, &f2); f4_mul(&t, &x->c, &f1); f4_add(&f3, &f3, &t); f4_times_i(&f3, &f3);
+    f4_mul(&t, &x->a, &f0); f4_add(&f3, &f3, &t); f4_inv(&f3, &f3);
+    f4_mul(&r->a, &f0, &f3); f4_mul(&r->b, &f1, &f3); f4_mul(&r->c, &f2, &f3);
+}
+static void f12_frob(fp12_t *r, const fp12_t *x) {                                 /* A/fp12.rs:757-771 */
+    fp2_t f2, f3;
+    f2_sqr(&f2, &FROB); f2_mul(&f3, &f2, &FROB);
+    f4_frob(&r->a, &x->a, &f3);
+    fp4_t t; f4_frob(&t, &x->b, &f3); f4_pmul(&r->b, &t, &FROB);
+    f4_frob(&t, &x->c, &f3); f4_pmul(&r->c, &t, &f2);
+}
+/* sparse product with a line (a.a, a.b, c.b non-zero: A/pair.rs:71-83) -- the reference's ssmul/smul
+ * (A/fp12.rs:371-707) exploit the same zeros */
+static void f12_mul_line(fp12_t *r, const fp12_t *x, const fp2_t *l0, const fp2_t *l3, const fp2_t *l5) {
+    fp4_t d, ad, bd, cd, af, bf, cf, t;
+    d.a = *l0; d.b = *l3;
+    f4_mul(&ad, &x->a, &d); f4_mul(&bd, &x->b, &d); f4_mul(&cd, &x->c, &d);
+    /* f = (0, l5) = j l5 :  u * f = times_i(u * l5) */
+    f4_pmul(&t, &x->a, l5); f4_times_i(&af, &t);
+    f4_pmul(&t, &x->b, l5); f4_times_i(&bf, &t);
+    f4_pmul(&t, &x->c, l5); f4_times_i(&cf, &t);
+    /* (a + b w + c w^2)(d + f w^2) = ad + j bf + (bd + j cf) w + (cd + af) w^2 */
+    f4_times_i(&t, &bf); f4_add(&r->a, &ad, &t);
+    f4_times_i(&t, &cf); f4_add(&r->b, &bd, &t);
+    f4_add(&r->c, &cd, &af);
+}
+static void f12_pow_x(fp12_t *r, const fp12_t *x, uint64_t e) {                    /* pow(|x|) then conj (A/pair.rs:490-529) */
+    fp12_t acc = *x; int top = 63; while (!((e >> top) & 1)) top--;
+    for (int i = top - 1; i >= 0; i--) { f12_sqr(&acc, &acc); if ((e >> i) & 1) f12_mul(&acc, &acc, x); }
+    f12_conj(r, &acc);
+}
+static void f12_to_bytes(uint8_t *out, const fp12_t *x) {                          /* A/fp12.rs:859-913 */
+    const fp_t *c = (const fp_t *)x;
+    for (int i = 0; i < 12; i++) fp_to_be(out + 48 * i, &c[i]);
+}
+
+/* ------------------------------------------------------------------------------------------------ groups */
+#define F fp_t
+#define FN(x) g1_##x
+#define F_ADD fp_add
+#define F_SUB fp_sub
+#define F_MUL fp_mul
+#define F_SQR fp_sqr
+#define F_NEG fp_neg
+#define F_INV fp_inv
+#define F_ISZERO fp_is_zero
+#define F_ONE(r) (*(r) = FP_ONE)
+#define F_ZERO(r) memset((r), 0, sizeof(fp_t))
+static void fp_mul_3b(fp_t *r, const fp_t *a) { fp_t t; fp_add(&t, a, a); fp_add(&t, &t, a); fp_add(&t, &t, &t); fp_add(r, &t, &t); }   /* 12 a */
+#define F_MUL_3B fp_mul_3b
+#include "ec_generic.inc"
+#undef F
+#undef FN
+#undef F_ADD
+#undef F_SUB
+#undef F_MUL
+#undef F_SQR
+#undef F_NEG
+#undef F_INV
+#undef F_ISZERO
+#undef F_ONE
+#undef F_ZERO
+#undef F_MUL_3B
+
+#define F fp2_t
+#define FN(x) g2_##x
+#define F_ADD f2_add
+#define F_SUB f2_sub
+#define F_MUL f2_mul
+#define F_SQR f2_sqr
+#define F_NEG f2_neg
+#define F_INV f2_inv
+#define F_ISZERO f2_is_zero
+#define F_ONE(r) f2_one(r)
+#define F_ZERO(r) f2_zero(r)
+static void f2_mul_3b(fp2_t *r, const fp2_t *a) { fp2_t t; f2_imul(&t, a, 12); f2_mul_ip(r, &t); }                                     /* 12 (1+i) a */
+#define F_MUL_3B f2_mul_3b
+#include "ec_generic.inc"
+
+static void g1_from_wire(g1_pt *p, const uint8_t *b) {
+    if (b[0] & 0x40) { g1_inf(p); return; }
+    fp_from_be(&p->x, b); fp_from_be(&p->y, b + 48); p->z = FP_ONE;
+}
+static void g1_to_wire(uint8_t *b, const g1_pt *q) {
+    g1_pt p = *q; g1_affine(&p);
+    if (g1_is_inf(&p)) { memset(b, 0, 96); b[0] = 0x40; return; }
+    fp_to_be(b, &p.x); fp_to_be(b + 48, &p.y);
+}
+static void g2_from_wire(g2_pt *p, const uint8_t *b) {
+    if (b[0] & 0x40) { g2_inf(p); return; }
+    fp_from_be(&p->x.b, b); fp_from_be(&p->x.a, b + 48); fp_from_be(&p->y.b, b + 96); fp_from_be(&p->y.a, b + 144); f2_one(&p->z);
+}
+static void g2_to_wire(uint8_t *b, const g2_pt *q) {
+    g2_pt p = *q; g2_affine(&p);
+    if (g2_is_inf(&p)) { memset(b, 0, 192); b[0] = 0x40; return; }
+    fp_to_be(b, &p.x.b); fp_to_be(b + 48, &p.x.a); fp_to_be(b + 96, &p.y.b); fp_to_be(b + 144, &p.y.a);
+}
+
+/* psi (A/ecp2.rs:538-548) with X = 1/FROB (A/ecp2.rs:785-789) */
+static void g2_frob_const(fp2_t *X) { f2_inv(X, &FROB); }      /* rebuilt by every caller, like the reference */
+static void g2_frob(g2_pt *p, const fp2_t *Xp) {
+    fp2_t X = *Xp, X2;
+    f2_sqr(&X2, &X);
+    f2_conj(&p->x, &p->x); f2_conj(&p->y, &p->y); f2_conj(&p->z, &p->z);
+    f2_mul(&p->x, &p->x, &X2); f2_mul(&p->y, &p->y, &X2); f2_mul(&p->y, &p->y, &X);
+}
+
+/* 256-bit helper arithmetic on scalars (4 x 64) */
+static int s_bits(const uint64_t *a) { for (int i = 255; i >= 0; i--) if ((a[i >> 6] >> (i & 63)) & 1) return i + 1; return 0; }
+static void s_sub(uint64_t *r, const uint64_t *a, const uint64_t *b) { u128 br = 0; for (int i = 0; i < 4; i++) { u128 t = (u128)a[i] - b[i] - br; r[i] = (uint64_t)t; br = (t >> 64) & 1; } }
+static void s_divmod_u64(uint64_t *q, uint64_t *rem, const uint64_t *a, uint64_t d) {
+    u128 r = 0; for (int i = 3; i >= 0; i--) { u128 cur = (r << 64) | a[i]; q[i] = (uint64_t)(cur / d); r = cur % d; } *rem = (uint64_t)r;
+}
+/* modneg (A/big.rs:1152-1156): r - (u mod r); u < r here, and r - 0 = r */
+static int s_geq(const uint64_t *a, const uint64_t *b) { for (int i = 3; i >= 0; i--) { if (a[i] > b[i]) return 1; if (a[i] < b[i]) return 0; } return 1; }
+static void s_modneg(uint64_t *r, const uint64_t *u) {
+    uint64_t um[4]; memcpy(um, u, 32);
+    while (s_geq(um, ORDER_R)) s_sub(um, um, ORDER_R);      /* u mod r (u <= r on this path) */
+    s_sub(r, ORDER_R, um);
+}
+/* "replace u by r - u and negate the point iff that has fewer bits" (A/pair.rs:635-649, 678-687) */
+static int s_signed_split(uint64_t *u) { uint64_t t[4]; s_modneg(t, u); if (s_bits(t) < s_bits(u)) { memcpy(u, t, 32); return 1; } return 0; }
+
+/* g2mul (A/pair.rs:661-693) with gs() (604-618) */
+static void pair_g2mul(g2_pt *r, const g2_pt *P, const uint64_t *e) {
+    uint64_t u[4][4] = {{0}}, w[4], q[4], rem;
+    memcpy(w, e, 32);
+    for (int i = 0; i < 3; i++) { s_divmod_u64(q, &rem, w, BNX); u[i][0] = rem; u[i][1] = u[i][2] = u[i][3] = 0; memcpy(w, q, 32); }
+    memcpy(u[3], w, 32);
+    s_modneg(u[1], u[1]); s_modneg(u[3], u[3]);
+    g2_pt Q[4]; Q[0] = *P;
+    fp2_t X; g2_frob_const(&X);
+    for (int i = 1; i < 4; i++) { Q[i] = Q[i - 1]; g2_frob(&Q[i], &X); }
+    for (int i = 0; i < 4; i++) if (s_signed_split(u[i])) g2_neg(&Q[i]);
+    g2_mul_joint(r, Q, (const uint64_t (*)[4])u, 4);
+}
+/* g1mul (A/pair.rs:625-656) with glv() (567-576): u0 = e mod x^2, u1 = r - e div x^2 */
+static void pair_g1mul(g1_pt *r, const g1_pt *P, const uint64_t *e) {
+    uint64_t u[2][4] = {{0}}, q1[4], q2[4], r0, r1;
+    s_divmod_u64(q1, &r0, e, BNX);                        /* e = q1 x + r0 */
+    s_divmod_u64(q2, &r1, q1, BNX);                       /* q1 = q2 x + r1 : e = q2 x^2 + r1 x + r0 */
+    u128 lo = (u128)r1 * BNX + r0;
+    u[0][0] = (uint64_t)lo; u[0][1] = (uint64_t)(lo >> 64);
+    s_modneg(u[1], q2);
+    g1_pt Q[2]; Q[0] = *P; Q[1] = *P; g1_affine(&Q[1]);
+    fp_mul(&Q[1].x, &Q[1].x, &CRU);
+    for (int i = 0; i < 2; i++) if (s_signed_split(u[i])) g1_neg(&Q[i]);
+    g1_mul_joint(r, Q, (const uint64_t (*)[4])u, 2);
+}
+static int subgroup_check_g2(const g2_pt *P) { g2_pt t; pair_g2mul(&t, P, ORDER_R); return g2_is_inf(&t); }      /* A/bls381/core.rs:123-127 */
+static int subgroup_check_g1(const g1_pt *P) { g1_pt t; pair_g1mul(&t, P, ORDER_R); return g1_is_inf(&t); }      /* :116-120 */
+
+/* ------------------------------------------------------------------------------------------------ SHA-256 + h2c */
+static const uint32_t K256[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be,
+    0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa,
+    0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85,
+    0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3,
+    0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f,
+    0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+#define ROR(x, n) (((x) >> (n)) | ((x) << (32 - (n))))
+static void sha256(uint8_t out[32], const uint8_t *msg, size_t len) {               /* A/hash256.rs:86-209 */
+    uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    size_t total = ((len + 9 + 63) / 64) * 64;
+    uint8_t *buf = (uint8_t *)calloc(total, 1);
+    memcpy(buf, msg, len); buf[len] = 0x80;
+    uint64_t bits = (uint64_t)len * 8;
+    for (int i = 0; i < 8; i++) buf[total - 1 - i] = (uint8_t)(bits >> (8 * i));
+    for (size_t off = 0; off < total; off += 64) {
+        uint32_t w[64];
+        for (int i = 0; i < 16; i++) w[i] = ((uint32_t)buf[off + 4 * i] << 24) | ((uint32_t)buf[off + 4 * i + 1] << 16) | ((uint32_t)buf[off + 4 * i + 2] << 8) | buf[off + 4 * i + 3];
+        for (int i = 16; i < 64; i++) { uint32_t s0 = ROR(w[i - 15], 7) ^ ROR(w[i - 15], 18) ^ (w[i - 15] >> 3), s1 = ROR(w[i - 2], 17) ^ ROR(w[i - 2], 19) ^ (w[i - 2] >> 10); w[i] = w[i - 16] + s0 + w[i - 7] + s1; }
+        uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+        for (int i = 0; i < 64; i++) {
+            uint32_t t1 = hh + (ROR(e, 6) ^ ROR(e, 11) ^ ROR(e, 25)) + ((e & f) ^ (~e & g)) + K256[i] + w[i];
+            uint32_t t2 = (ROR(a, 2) ^ ROR(a, 13) ^ ROR(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+            hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        }
+        h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+    }
+    free(buf);
+    for (int i = 0; i < 8; i++) { out[4 * i] = (uint8_t)(h[i] >> 24); out[4 * i + 1] = (uint8_t)(h[i] >> 16); out[4 * i + 2] = (uint8_t)(h[i] >> 8); out[4 * i + 3] = (uint8_t)h[i]; }
+}
+static void expand_message_xmd_256(uint8_t out[256], const uint8_t *msg, size_t len, const uint8_t *dst, size_t dlen) {   /* A/hash_to_curve.rs:137-201 */
+    size_t tl = 64 + len + 3 + dlen + 1;
+    uint8_t *tmp = (uint8_t *)calloc(tl, 1);
+    memcpy(tmp + 64, msg, len); tmp[64 + len] = 0x01; tmp[64 + len + 1] = 0x00; tmp[64 + len + 2] = 0x00;
+    memcpy(tmp + 64 + len + 3, dst, dlen); tmp[tl - 1] = (uint8_t)dlen;
+    uint8_t b0[32], bi[32] = {0}, blk[32 + 1 + 256];
+    sha256(b0, tmp, tl); free(tmp);
+    for (int k = 1; k <= 8; k++) {
+        for (int j = 0; j < 32; j++) blk[j] = b0[j] ^ bi[j];
+        blk[32] = (uint8_t)k; memcpy(blk + 33, dst, dlen); blk[33 + dlen] = (uint8_t)dlen;
+        sha256(bi, blk, 34 + dlen);
+        memcpy(out + 32 * (k - 1), bi, 32);
+    }
+}
+static void fp_from_be64(fp_t *r, const uint8_t *b) {                              /* DBig::from_bytes + dmod, A/dbig.rs:174-207,294-310 */
+    /* value = hi * 2^384 + lo -> Montgomery: lo*R + hi*R^2 */
+    fp_t lo, hi = {{0}}, t;
+    for (int i = 0; i < 6; i++) { uint64_t v = 0; for (int k = 0; k < 8; k++) v = (v << 8) | b[16 + 40 - 8 * i + k]; lo.l[i] = v; }
+    for (int i = 0; i < 2; i++) { uint64_t v = 0; for (int k = 0; k < 8; k++) v = (v << 8) | b[8 - 8 * i + k]; hi.l[i] = v; }
+    while (raw_geq(lo.l, FP_P.l)) raw_sub(lo.l, lo.l, FP_P.l);
+    fp_to_mont(&lo, &lo);
+    fp_to_mont(&t, &hi); fp_to_mont(&t, &t);            /* hi * R * R */
+    fp_add(r, &lo, &t);
+}
+static void sswu_gx(fp2_t *g, const fp2_t *x) { fp2_t t; f2_sqr(&t, x); f2_add(&t, &t, &SSWU_A); f2_mul(&t, &t, x); f2_add(g, &t, &SSWU_B); }
+static void simplified_swu_fp2(fp2_t *xo, fp2_t *yo, const fp2_t *u) {            /* A/hash_to_curve.rs:283-346 */
+    fp2_t tmp1, tv1, x, ainv, one, gx, y;
+    f2_one(&one);
+    f2_sqr(&tmp1, u); f2_mul(&tmp1, &tmp1, &SSWU_Z);
+    f2_sqr(&tv1, &tmp1); f2_add(&tv1, &tv1, &tmp1); f2_inv(&tv1, &tv1);
+    f2_add(&x, &tv1, &one); f2_mul(&x, &x, &SSWU_B); f2_neg(&x, &x);
+    f2_inv(&ainv, &SSWU_A); f2_mul(&x, &x, &ainv);
+    if (f2_is_zero(&tv1)) { f2_inv(&x, &SSWU_Z); f2_mul(&x, &x, &SSWU_B); f2_mul(&x, &x, &ainv); }
+    sswu_gx(&gx, &x); y = gx;
+    if (!f2_sqrt(&y)) { f2_mul(&x, &x, &tmp1); sswu_gx(&gx, &x); y = gx; f2_sqrt(&y); }
+    if (f2_sgn0(u) != f2_sgn0(&y)) f2_neg(&y, &y);
+    *xo = x; *yo = y;
+}
+static void iso3_to_ecp2(g2_pt *r, const fp2_t *x, const fp2_t *y) {              /* A/bls381/iso.rs:177-206 */
+    const fp2_t *polys[4] = {ISO3_XNUM, ISO3_XDEN, ISO3_YNUM, ISO3_YDEN};
+    fp2_t v[4];
+    for (int i = 0; i < 4; i++) { v[i] = polys[i][3]; for (int k = 2; k >= 0; k--) { f2_mul(&v[i], &v[i], x); f2_add(&v[i], &v[i], &polys[i][k]); } }
+    f2_mul(&v[2], &v[2], y);
+    f2_mul(&r->z, &v[1], &v[3]); f2_mul(&r->x, &v[0], &v[3]); f2_mul(&r->y, &v[2], &v[1]);
+}
+static void g2_clear_cofactor(g2_pt *P) {                                          /* A/ecp2.rs:784-805 */
+    uint64_t x[1] = {BNX};
+    g2_pt xQ, x2Q, t;
+    fp2_t X; g2_frob_const(&X);
+    g2_mul(&xQ, P, x, 1); g2_mul(&x2Q, &xQ, x, 1);
+    g2_neg(&xQ);
+    t = xQ; g2_neg(&t); g2_add(&x2Q, &t);
+    t = *P; g2_neg(&t); g2_add(&x2Q, &t);
+    g2_add(&xQ, &t);
+    g2_frob(&xQ, &X);
+    g2_dbl(P); g2_frob(P, &X); g2_frob(P, &X);
+    g2_add(P, &x2Q); g2_add(P, &xQ);
+    g2_affine(P);
+}
+static const uint8_t DST_G2[] = "BLS_SIG_BLS12381G2_XMD:SHA-256_SSWU_RO_POP_";
+static void hash_to_curve_g2(g2_pt *r, const uint8_t *msg, size_t len, const uint8_t *dst, size_t dlen) {   /* A/bls381/core.rs:831-849 */
+    uint8_t prb[256];
+    expand_message_xmd_256(prb, msg, len, dst, dlen);
+    fp2_t u[2];
+    for (int i = 0; i < 2; i++) { fp_from_be64(&u[i].a, prb + 128 * i); fp_from_be64(&u[i].b, prb + 128 * i + 64); }
+    g2_pt q0, q1; fp2_t x, y;
+    simplified_swu_fp2(&x, &y, &u[0]); iso3_to_ecp2(&q0, &x, &y);
+    simplified_swu_fp2(&x, &y, &u[1]); iso3_to_ecp2(&q1, &x, &y);
+    g2_add(&q0, &q1);
+    g2_clear_cofactor(&q0);
+    *r = q0;
+}
+
+/* ------------------------------------------------------------------------------------------------ pairing */
+#define ATE_BITS 65
+static void linedbl(fp2_t *l0, fp2_t *l3, fp2_t *l5, g2_pt *A, const fp_t *qx, const fp_t *qy) {   /* A/pair.rs:35-84 */
+    fp2_t xx = A->x, yy = A->y, zz = A->z, yz = A->y;
+    f2_mul(&yz, &yz, &zz); f2_sqr(&xx, &xx); f2_sqr(&yy, &yy); f2_sqr(&zz, &zz);
+    f2_imul(&yz, &yz, 4); f2_neg(&yz, &yz); f2_pmul(&yz, &yz, qy);
+    f2_imul(&xx, &xx, 6); f2_pmul(&xx, &xx, qx);
+    f2_imul(&zz, &zz, 12); f2_mul_ip(&zz, &zz); f2_add(&zz, &zz, &zz);
+    f2_mul_ip(&yz, &yz);
+    f2_add(&yy, &yy, &yy); f2_sub(&zz, &zz, &yy);
+    *l0 = yz; *l3 = zz; *l5 = xx;
+    g2_dbl(A);
+}
+static void lineadd(fp2_t *l0, fp2_t *l3, fp2_t *l5, g2_pt *A, const g2_pt *B, const fp_t *qx, const fp_t *qy) {   /* A/pair.rs:88-133 */
+    fp2_t x1 = A->x, y1 = A->y, t1 = A->z, t2 = A->z;
+    f2_mul(&t1, &t1, &B->y); f2_mul(&t2, &t2, &B->x);
+    f2_sub(&x1, &x1, &t2); f2_sub(&y1, &y1, &t1);
+    t1 = x1; f2_pmul(&x1, &x1, qy); f2_mul_ip(&x1, &x1);
+    f2_mul(&t1, &t1, &B->y);
+    t2 = y1; f2_mul(&t2, &t2, &B->x); f2_sub(&t2, &t2, &t1);
+    f2_pmul(&y1, &y1, qx); f2_neg(&y1, &y1);
+    *l0 = x1; *l3 = t2; *l5 = y1;
+    g2_add(A, B);
+}
+static void line_to_f12(fp12_t *r, const fp2_t *l0, const fp2_t *l3, const fp2_t *l5) {
+    memset(r, 0, sizeof(*r)); r->a.a = *l0; r->a.b = *l3; r->c.b = *l5;        /* c = times_i(FP4(l5)) = (0, l5) */
+}
+static void initmp(fp12_t *rr) { for (int i = 0; i < ATE_BITS; i++) f12_one(&rr[i]); }
+/* another (A/pair.rs:182-238): P in G2, Q in G1, both made affine here */
+static void another(fp12_t *rr, const g2_pt *P1, const g1_pt *Q1) {
+    g2_pt P = *P1; g2_affine(&P);
+    g1_pt Q = *Q1; g1_affine(&Q);
+    if (g2_is_inf(&P) || g1_is_inf(&Q)) return;            /* contributes only subfield factors */
+    g2_pt A = P, NP = P; g2_neg(&NP);
+    u128 n = BNX, n3 = (u128)BNX * 3;
+    int nb = 0; while ((n3 >> nb) != 0) nb++;
+    for (int i = nb - 2; i >= 1; i--) {
+        fp2_t l0, l3, l5; fp12_t lv, lv2;
+        linedbl(&l0, &l3, &l5, &A, &Q.x, &Q.y);
+        int bt = (int)((n3 >> i) & 1) - (int)((n >> i) & 1);
+        if (bt == 0) { f12_mul_line(&rr[i], &rr[i], &l0, &l3, &l5); continue; }
+        line_to_f12(&lv, &l0, &l3, &l5);
+        lineadd(&l0, &l3, &l5, &A, bt == 1 ? &P : &NP, &Q.x, &Q.y);
+        f12_mul_line(&lv2, &lv, &l0, &l3, &l5);            /* lv.smul(lv2) */
+        f12_mul(&rr[i], &rr[i], &lv2);
+    }
+}
+static void miller(fp12_t *res, const fp12_t *rr) {                               /* A/pair.rs:166-178 */
+    f12_one(res);
+    for (int i = ATE_BITS - 1; i >= 1; i--) { f12_sqr(res, res); f12_mul(res, res, &rr[i]); }
+    f12_conj(res, res);
+    f12_mul(res, res, &rr[0]);
+}
+static void fexp(fp12_t *out, const fp12_t *m) {                                   /* A/pair.rs:409-541, BLS branch */
+    fp12_t r, lv, y0, y1, y2, y3;
+    f12_inv(&lv, m); f12_conj(&r, m); f12_mul(&r, &r, &lv);
+    lv = r; f12_frob(&r, &r); f12_frob(&r, &r); f12_mul(&r, &r, &lv);
+    f12_sqr(&y0, &r);
+    f12_pow_x(&y1, &y0, BNX);
+    f12_pow_x(&y2, &y1, BNX >> 1);
+    f12_conj(&y3, &r); f12_mul(&y1, &y1, &y3);
+    f12_conj(&y1, &y1); f12_mul(&y1, &y1, &y2);
+    f12_pow_x(&y2, &y1, BNX);
+    f12_pow_x(&y3, &y2, BNX);
+    f12_conj(&y1, &y1); f12_mul(&y3, &y3, &y1);
+    f12_conj(&y1, &y1);
+    f12_frob(&y1, &y1); f12_frob(&y1, &y1); f12_frob(&y1, &y1);
+    f12_frob(&y2, &y2); f12_frob(&y2, &y2);
+    f12_mul(&y1, &y1, &y2);
+    f12_pow_x(&y2, &y3, BNX);
+    f12_mul(&y2, &y2, &y0); f12_mul(&y2, &y2, &r);
+    f12_mul(&y1, &y1, &y2);
+    f12_frob(&y2, &y3); f12_mul(out, &y1, &y2);
+}
+
+/* ------------------------------------------------------------------------------------------------ exported API */
+static void neg_g1_gen(g1_pt *g) { g->x = G1X; g->y = G1Y; g->z = FP_ONE; g1_neg(g); }
+
+int oc_hash_to_g2(const uint8_t *msg, size_t len, const uint8_t *dst, size_t dlen, uint8_t out192[192]) {
+    g2_pt p;
+    if (!dst) { dst = DST_G2; dlen = 43; }
+    hash_to_curve_g2(&p, msg, len, dst, dlen);
+    g2_to_wire(out192, &p);
+    return 0;
+}
+/* AggregatePublicKey::into_aggregate (M/src/aggregates.rs:46-56) */
+int oc_g1_aggregate(const uint8_t *pks96, size_t n, uint8_t out96[96]) {
+    if (n == 0) return -1;
+    g1_pt acc, p; g1_inf(&acc);
+    for (size_t i = 0; i < n; i++) { g1_from_wire(&p, pks96 + 96 * i); g1_add(&acc, &p); }
+    g1_to_wire(out96, &acc);
+    return 0;
+}
+int oc_subgroup_check_g2(const uint8_t *p192) { g2_pt p; g2_from_wire(&p, p192); return subgroup_check_g2(&p); }
+int oc_subgroup_check_g1(const uint8_t *p96) { g1_pt p; g1_from_wire(&p, p96); return subgroup_check_g1(&p); }
+int oc_g1_mul(const uint8_t *p96, const uint8_t k32[32], uint8_t out96[96]) {
+    g1_pt p, r; uint64_t k[4];
+    for (int i = 0; i < 4; i++) { uint64_t v = 0; for (int j = 0; j < 8; j++) v = (v << 8) | k32[24 - 8 * i + j]; k[i] = v; }
+    g1_from_wire(&p, p96); g1_mul(&r, &p, k, 4); g1_to_wire(out96, &r);
+    return 0;
+}
+int oc_g2_mul(const uint8_t *p192, const uint8_t k32[32], uint8_t out192[192]) {
+    g2_pt p, r; uint64_t k[4];
+    for (int i = 0; i < 4; i++) { uint64_t v = 0; for (int j = 0; j < 8; j++) v = (v << 8) | k32[24 - 8 * i + j]; k[i] = v; }
+    g2_from_wire(&p, p192); g2_mul(&r, &p, k, 4); g2_to_wire(out192, &r);
+    return 0;
+}
+/* verify_multiple_aggregate_signatures (M/src/aggregates.rs:261-316).  Set j: sig_j, apk_j (pk_off == NULL) or the
+ * keys pks96[pk_off[j]..pk_off[j+1]) aggregated first (the C4 shape), msg_j, scalar_j.  Returns accept. */
+int oc_verify_multiple(const uint8_t *sigs192, const uint8_t *pks96, const uint32_t *pk_off, const uint8_t *msgs, const uint32_t *msg_off,
+                       const uint64_t *scalars, size_t n, uint8_t *gt576) {
+    fp12_t *rr = (fp12_t *)malloc(sizeof(fp12_t) * ATE_BITS);
+    initmp(rr);
+    g2_pt final_sig; g2_inf(&final_sig);
+    int ok = 1;
+    for (size_t j = 0; j < n && ok; j++) {
+        g2_pt sig; g2_from_wire(&sig, sigs192 + 192 * j);
+        if (!subgroup_check_g2(&sig)) { ok = 0; break; }
+        g1_pt apk;
+        if (pk_off) { g1_pt p; g1_inf(&apk); for (uint32_t i = pk_off[j]; i < pk_off[j + 1]; i++) { g1_from_wire(&p, pks96 + 96 * (size_t)i); g1_add(&apk, &p); } }
+        else g1_from_wire(&apk, pks96 + 96 * j);
+        uint64_t c[4] = {scalars[j], 0, 0, 0};
+        g2_pt H; hash_to_curve_g2(&H, msgs + msg_off[j], msg_off[j + 1] - msg_off[j], DST_G2, 43);
+        g1_pt capk; pair_g1mul(&capk, &apk, c);
+        another(rr, &H, &capk);
+        g2_pt csig; pair_g2mul(&csig, &sig, c);
+        g2_add(&final_sig, &csig);
+    }
+    int accept = 0;
+    if (ok) {
+        g1_pt ng; neg_g1_gen(&ng);
+        another(rr, &final_sig, &ng);
+        fp12_t v, gt; miller(&v, rr); fexp(&gt, &v);
+        accept = f12_is_one(&gt);
+        if (gt576) f12_to_bytes(gt576, &gt);
+    }
+    free(rr);
+    return accept;
+}
+/* fast_aggregate_verify (M/src/aggregates.rs:177-215) / Signature::verify (n = 1, no infinity check) */
+int oc_fast_aggregate_verify(const uint8_t *sig192, const uint8_t *pks96, size_t n, const uint8_t *msg, size_t len, int reject_inf, uint8_t *gt576) {
+    if (n == 0) return 0;
+    g2_pt sig; g2_from_wire(&sig, sig192);
+    if (!subgroup_check_g2(&sig)) return 0;
+    g1_pt apk, p; g1_inf(&apk);
+    for (size_t i = 0; i < n; i++) { g1_from_wire(&p, pks96 + 96 * i); g1_add(&apk, &p); }
+    if (reject_inf && g1_is_inf(&apk)) return 0;
+    g2_pt H; hash_to_curve_g2(&H, msg, len, DST_G2, 43);
+    fp12_t *rr = (fp12_t *)malloc(sizeof(fp12_t) * ATE_BITS);
+    initmp(rr);
+    g1_pt ng; neg_g1_gen(&ng);
+    another(rr, &sig, &ng); another(rr, &H, &apk);
+    fp12_t v, gt; miller(&v, rr); fexp(&gt, &v);
+    free(rr);
+    if (gt576) f12_to_bytes(gt576, &gt);
+    return f12_is_one(&gt);
+}
+/* aggregate_verify (M/src/aggregates.rs:130-170) */
+int oc_aggregate_verify(const uint8_t *sig192, const uint8_t *pks96, const uint8_t *msgs, const uint32_t *msg_off, size_t n, uint8_t *gt576) {
+    if (n == 0) return 0;
+    g2_pt sig; g2_from_wire(&sig, sig192);
+    if (!subgroup_check_g2(&sig)) return 0;
+    fp12_t *rr = (fp12_t *)malloc(sizeof(fp12_t) * ATE_BITS);
+    initmp(rr);
+    for (size_t i = 0; i < n; i++) {
+        g2_pt H; hash_to_curve_g2(&H, msgs + msg_off[i], msg_off[i + 1] - msg_off[i], DST_G2, 43);
+        g1_pt pk; g1_from_wire(&pk, pks96 + 96 * i);
+        another(rr, &H, &pk);
+    }
+    g1_pt ng; neg_g1_gen(&ng);
+    another(rr, &sig, &ng);
+    fp12_t v, gt; miller(&v, rr); fexp(&gt, &v);
+    free(rr);
+    if (gt576) f12_to_bytes(gt576, &gt);
+    return f12_is_one(&gt);
+}
+/* e(Q, P) after the final exponentiation (tests) */
+int oc_pairing(const uint8_t *q192, const uint8_t *p96, uint8_t gt576[576]) {
+    g2_pt Q; g1_pt P; g2_from_wire(&Q, q192); g1_from_wire(&P, p96);
+    fp12_t *rr = (fp12_t *)malloc(sizeof(fp12_t) * ATE_BITS);
+    initmp(rr); another(rr, &Q, &P);
+    fp12_t v, gt; miller(&v, rr); fexp(&gt, &v);
+    free(rr);
+    f12_to_bytes(gt576, &gt);
+    return f12_is_one(&gt);
+}
