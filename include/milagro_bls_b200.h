@@ -55,6 +55,9 @@ float b3_ctx_last_kernel_ms(b3_ctx* ctx, int which);
  * stages 0 .. b3_stage_count()-1 are named by b3_stage_name() */
 float b3_ctx_stage_ms(b3_ctx* ctx, int stage);
 const char* b3_stage_name(int stage);
+/* serial != 0: run the independent stages of a verification call one after another on the context's stream (for
+ * per-stage timing); default 0: they overlap on internal streams, joined before the Miller loop */
+void b3_ctx_set_serial(b3_ctx* ctx, int serial);
 int b3_stage_count(void);
 
 /* ---- (de)serialisation: PublicKey::{from_bytes, from_bytes_unchecked, as_bytes} (M/src/keys.rs:140-160),

@@ -92,6 +92,10 @@ class Engine:
     def last_kernel_ms(self, which=0):
         return float(self.L.b3_ctx_last_kernel_ms(self.handle, which))
 
+    def set_serial(self, serial=True):
+        """serial=True: independent stages run one after another (per-stage timing); False: overlapped (default)."""
+        self.L.b3_ctx_set_serial(self.handle, 1 if serial else 0)
+
     def stage_ms(self):
         """{stage name: device ms} of the most recent verification / hash call (CUDA events on the library's stream)."""
         return {self.L.b3_stage_name(i).decode(): float(self.L.b3_ctx_stage_ms(self.handle, i)) for i in range(self.L.b3_stage_count())}

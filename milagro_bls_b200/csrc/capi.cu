@@ -22,7 +22,7 @@ static const size_t kDstG2Len = 43;
 // stage ids (b3_ctx_stage_ms / b3_stage_name)
 enum { ST_SIG_CHECK = 0, ST_AGGREGATE, ST_G1_MUL, ST_HASH_TO_G2, ST_G2_MUL_SUM, ST_MILLER, ST_FP12_PRODUCT, ST_FINAL_EXP, ST_COPY, ST_END };
 static const char* kStageNames[B3_N_STAGES] = {"g2_parse_subgroup_check", "g1_aggregate", "g1_scalar_mul_affine", "hash_to_g2_affine",
-                                               "g2_scalar_mul_sum", "miller_loop", "fp12_product_tree", "final_exp", "copies", "end"};
+                                               "g2_scalar_mul_sum", "miller_loop", "fp12_product_tree", "final_exp", "parse_copies", "end"};
 
 struct dev_buf {
     void* p = nullptr;
@@ -36,14 +36,18 @@ struct b3_ctx {
     uint64_t launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // 0/1: whole call, 2/3: Miller kernel
     float last_ms[2] = {0.f, 0.f};
-    // stage marks of the most recent verification call: mark i opens stage mark_id[i]; the last mark closes the call
-    cudaEvent_t mark_ev[B3_MAX_MARKS];
-    int mark_id[B3_MAX_MARKS];
-    int n_marks = 0;
+    // stage spans of the most recent verification call: span i = [span_a[i], span_b[i]] on the stream the stage ran on
+    cudaEvent_t span_a[B3_MAX_MARKS], span_b[B3_MAX_MARKS];
+    int span_id[B3_MAX_MARKS];
+    int n_spans = 0;
     float stage_ms[B3_N_STAGES];
+    // independent stages of verify_multiple run concurrently on aux streams (fork/join by events) unless serial != 0
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_fork2 = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    int serial = 0;
     // scratch (grown on demand, reused across calls)
     dev_buf in_a, in_b, in_c, in_d, in_e, in_f;      // staged host inputs
-    dev_buf g1j, g1j2, g1a, g2a_sig, g2j, g2j2, g2a, f12a, f12b, status, ok, misc, outb;
+    dev_buf g1j, g1j2, g1a, g2a_sig, g2j, g2j2, g2j_h, g2a, f12a, f12b, status, ok, misc, outb;
     uint8_t* d_dst = nullptr;
 };
 
@@ -78,6 +82,12 @@ static inline unsigned nblk(size_t n, int tpb = B3_TPB) { return (unsigned)((n +
         ctx->launches++;                                     \
     } while (0)
 
+#define LAUNCH_ON(strm, kern, grid, block, ...)              \
+    do {                                                     \
+        kern<<<(grid), (block), 0, (strm)>>>(__VA_ARGS__);   \
+        ctx->launches++;                                     \
+    } while (0)
+
 extern "C" int b3_ctx_create(int device, b3_ctx** out) {
     if (!out) return B3_ERR_ARG;
     *out = nullptr;
@@ -91,7 +101,13 @@ extern "C" int b3_ctx_create(int device, b3_ctx** out) {
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B3_ERR_CUDA; }
     for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
-    for (int i = 0; i < B3_MAX_MARKS; i++) cudaEventCreate(&ctx->mark_ev[i]);
+    for (int i = 0; i < B3_MAX_MARKS; i++) { cudaEventCreate(&ctx->span_a[i]); cudaEventCreate(&ctx->span_b[i]); }
+    for (int i = 0; i < 3; i++) {
+        if (cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B3_ERR_CUDA; }
+        cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming);
     for (int i = 0; i < B3_N_STAGES; i++) ctx->stage_ms[i] = 0.f;
     if (cudaMalloc((void**)&ctx->d_dst, 256) != cudaSuccess) { delete ctx; return B3_ERR_CUDA; }
     cudaMemcpy(ctx->d_dst, kDstG2, kDstG2Len, cudaMemcpyHostToDevice);
@@ -103,12 +119,15 @@ extern "C" void b3_ctx_destroy(b3_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     dev_buf* bufs[] = {&ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->in_d, &ctx->in_e, &ctx->in_f, &ctx->g1j, &ctx->g1j2, &ctx->g1a,
-                       &ctx->g2a_sig, &ctx->g2j, &ctx->g2j2, &ctx->g2a, &ctx->f12a, &ctx->f12b, &ctx->status, &ctx->ok,
+                       &ctx->g2a_sig, &ctx->g2j, &ctx->g2j2, &ctx->g2j_h, &ctx->g2a, &ctx->f12a, &ctx->f12b, &ctx->status, &ctx->ok,
                        &ctx->misc, &ctx->outb};
     for (dev_buf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_dst) cudaFree(ctx->d_dst);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-    for (int i = 0; i < B3_MAX_MARKS; i++) cudaEventDestroy(ctx->mark_ev[i]);
+    for (int i = 0; i < B3_MAX_MARKS; i++) { cudaEventDestroy(ctx->span_a[i]); cudaEventDestroy(ctx->span_b[i]); }
+    for (int i = 0; i < 3; i++) { cudaStreamSynchronize(ctx->aux[i]); cudaStreamDestroy(ctx->aux[i]); cudaEventDestroy(ctx->ev_join[i]); }
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_fork2);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -119,18 +138,25 @@ extern "C" float b3_ctx_last_kernel_ms(b3_ctx* ctx, int which) { return (ctx && 
 extern "C" float b3_ctx_stage_ms(b3_ctx* ctx, int stage) { return (ctx && stage >= 0 && stage < B3_N_STAGES) ? ctx->stage_ms[stage] : 0.f; }
 extern "C" const char* b3_stage_name(int stage) { return (stage >= 0 && stage < B3_N_STAGES) ? kStageNames[stage] : ""; }
 extern "C" int b3_stage_count(void) { return B3_N_STAGES - 1; }
-static void mark_reset(b3_ctx* ctx) { ctx->n_marks = 0; }
-static void mark(b3_ctx* ctx, int id) {
-    if (ctx->n_marks >= B3_MAX_MARKS) return;
-    cudaEventRecord(ctx->mark_ev[ctx->n_marks], ctx->stream);
-    ctx->mark_id[ctx->n_marks++] = id;
+extern "C" void b3_ctx_set_serial(b3_ctx* ctx, int serial) { if (ctx) ctx->serial = serial; }
+static void mark_reset(b3_ctx* ctx) { ctx->n_spans = 0; }
+// open a stage span on `strm`; returns the span index (or -1 when the table is full)
+static int span_begin(b3_ctx* ctx, int id, cudaStream_t strm) {
+    if (ctx->n_spans >= B3_MAX_MARKS) return -1;
+    int i = ctx->n_spans++;
+    ctx->span_id[i] = id;
+    cudaEventRecord(ctx->span_a[i], strm);
+    return i;
 }
-// after a stream synchronize: fold the marks into per-stage durations
+static void span_end(b3_ctx* ctx, int i, cudaStream_t strm) {
+    if (i >= 0) cudaEventRecord(ctx->span_b[i], strm);
+}
+// after a stream synchronize: fold the spans into per-stage durations
 static void mark_collect(b3_ctx* ctx) {
     for (int i = 0; i < B3_N_STAGES; i++) ctx->stage_ms[i] = 0.f;
-    for (int i = 0; i + 1 < ctx->n_marks; i++) {
+    for (int i = 0; i < ctx->n_spans; i++) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, ctx->mark_ev[i], ctx->mark_ev[i + 1]) == cudaSuccess) ctx->stage_ms[ctx->mark_id[i]] += ms;
+        if (cudaEventElapsedTime(&ms, ctx->span_a[i], ctx->span_b[i]) == cudaSuccess) ctx->stage_ms[ctx->span_id[i]] += ms;
     }
     cudaGetLastError();
 }
@@ -190,20 +216,23 @@ static int miller_product(b3_ctx* ctx, const g2_aff* q, const g1_aff* p, size_t 
         return B3_OK;
     }
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-    mark(ctx, ST_MILLER);
+    int sp = span_begin(ctx, ST_MILLER, ctx->stream);
     LAUNCH(k_miller, nblk(n_pairs), B3_TPB, q, p, n_pairs, fa);
+    span_end(ctx, sp, ctx->stream);
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-    mark(ctx, ST_FP12_PRODUCT);
-    return fp12_product(ctx, fa, (fp12*)ctx->f12b.p, n_pairs, res);
+    sp = span_begin(ctx, ST_FP12_PRODUCT, ctx->stream);
+    int rc = fp12_product(ctx, fa, (fp12*)ctx->f12b.p, n_pairs, res);
+    span_end(ctx, sp, ctx->stream);
+    return rc;
 }
 // final exponentiation of *m -> accept / gt on the host
 static int finish(b3_ctx* ctx, const fp12* m, int* accept, uint8_t* gt576) {
     CKR(ensure(ctx, ctx->outb, 576 + 16));
     uint8_t* d_gt = (uint8_t*)ctx->outb.p;
     int32_t* d_one = (int32_t*)(d_gt + 576);
-    mark(ctx, ST_FINAL_EXP);
-    LAUNCH(k_final_exp, 1, 1, m, d_gt, d_one);
-    mark(ctx, ST_END);
+    int sp = span_begin(ctx, ST_FINAL_EXP, ctx->stream);
+    LAUNCH(k_final_exp, 1, B3_COOP_THREADS, m, d_gt, d_one);
+    span_end(ctx, sp, ctx->stream);
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     int32_t one = 0;
     uint8_t gt[576];
@@ -376,11 +405,11 @@ static int stage_dst(b3_ctx* ctx, const uint8_t* dst, size_t dst_len, const uint
     *len = (uint32_t)dst_len;
     return B3_OK;
 }
-static int hash_to_g2_affine_dev(b3_ctx* ctx, const uint8_t* d_msgs, const uint32_t* d_off, size_t n, const uint8_t* d_dst, uint32_t dst_len,
-                                 g2_aff* d_out) {
-    CKR(ensure(ctx, ctx->g2j, sizeof(g2_jac) * n));
-    LAUNCH(k_hash_to_g2, nblk(n), B3_TPB, d_msgs, d_off, n, d_dst, dst_len, (g2_jac*)ctx->g2j.p);
-    LAUNCH(k_g2_to_affine, nblk(n), B3_TPB, (const g2_jac*)ctx->g2j.p, n, d_out);
+static int hash_to_g2_affine_dev(b3_ctx* ctx, cudaStream_t strm, const uint8_t* d_msgs, const uint32_t* d_off, size_t n, const uint8_t* d_dst,
+                                 uint32_t dst_len, g2_aff* d_out) {
+    CKR(ensure(ctx, ctx->g2j_h, sizeof(g2_jac) * n));
+    LAUNCH_ON(strm, k_hash_to_g2, nblk(n), B3_TPB, d_msgs, d_off, n, d_dst, dst_len, (g2_jac*)ctx->g2j_h.p);
+    LAUNCH_ON(strm, k_g2_to_affine, nblk(n), B3_TPB, (const g2_jac*)ctx->g2j_h.p, n, d_out);
     return B3_OK;
 }
 extern "C" int b3_hash_to_g2_dev(b3_ctx* ctx, const uint8_t* msgs_dev, const uint32_t* off_dev, size_t n, uint8_t* out192_dev) {
@@ -389,11 +418,12 @@ extern "C" int b3_hash_to_g2_dev(b3_ctx* ctx, const uint8_t* msgs_dev, const uin
     CKR(ensure(ctx, ctx->g2a, sizeof(g2_aff) * n));
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     mark_reset(ctx);
-    mark(ctx, ST_HASH_TO_G2);
-    CKR(hash_to_g2_affine_dev(ctx, msgs_dev, off_dev, n, ctx->d_dst, (uint32_t)kDstG2Len, (g2_aff*)ctx->g2a.p));
-    mark(ctx, ST_COPY);
+    int sp = span_begin(ctx, ST_HASH_TO_G2, ctx->stream);
+    CKR(hash_to_g2_affine_dev(ctx, ctx->stream, msgs_dev, off_dev, n, ctx->d_dst, (uint32_t)kDstG2Len, (g2_aff*)ctx->g2a.p));
+    span_end(ctx, sp, ctx->stream);
+    sp = span_begin(ctx, ST_COPY, ctx->stream);
     LAUNCH(k_g2_aff_to_wire, nblk(n), B3_TPB, (const g2_aff*)ctx->g2a.p, n, out192_dev);
-    mark(ctx, ST_END);
+    span_end(ctx, sp, ctx->stream);
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     CKR(sync(ctx));
     mark_collect(ctx);
@@ -411,7 +441,7 @@ extern "C" int b3_hash_to_g2(b3_ctx* ctx, const uint8_t* msgs, const uint32_t* o
     CKR(h2d(ctx, ctx->in_b, off, 4 * (n + 1)));
     CKR(ensure(ctx, ctx->g2a, sizeof(g2_aff) * n));
     CKR(ensure(ctx, ctx->outb, 192 * n));
-    CKR(hash_to_g2_affine_dev(ctx, (const uint8_t*)ctx->in_a.p, (const uint32_t*)ctx->in_b.p, n, d_dst, dl, (g2_aff*)ctx->g2a.p));
+    CKR(hash_to_g2_affine_dev(ctx, ctx->stream, (const uint8_t*)ctx->in_a.p, (const uint32_t*)ctx->in_b.p, n, d_dst, dl, (g2_aff*)ctx->g2a.p));
     LAUNCH(k_g2_aff_to_wire, nblk(n), B3_TPB, (const g2_aff*)ctx->g2a.p, n, (uint8_t*)ctx->outb.p);
     CKR(d2h(ctx, out192, ctx->outb.p, 192 * n));
     return sync(ctx);
@@ -433,7 +463,7 @@ static int verify_two_pairs(b3_ctx* ctx, const g2_aff* d_sig, const int32_t* d_s
     CK(cudaMemcpyAsync(q, d_sig, sizeof(g2_aff), cudaMemcpyDeviceToDevice, ctx->stream));
     LAUNCH(k_set_neg_g1, 1, 1, p);
     // pair 1: (H(msg), key)
-    CKR(hash_to_g2_affine_dev(ctx, (const uint8_t*)ctx->in_c.p, (const uint32_t*)ctx->in_d.p, 1, ctx->d_dst, (uint32_t)kDstG2Len, q + 1));
+    CKR(hash_to_g2_affine_dev(ctx, ctx->stream, (const uint8_t*)ctx->in_c.p, (const uint32_t*)ctx->in_d.p, 1, ctx->d_dst, (uint32_t)kDstG2Len, q + 1));
     LAUNCH(k_g1_to_affine, 1, B3_TPB, d_key, 1, p + 1);
     fp12* res;
     CKR(miller_product(ctx, q, p, 2, &res));
@@ -521,7 +551,7 @@ extern "C" int b3_aggregate_verify(b3_ctx* ctx, const uint8_t sig192[192], const
     g2_aff* q = (g2_aff*)ctx->g2a.p;
     g1_aff* p = (g1_aff*)ctx->g1a.p;
     LAUNCH(k_g1_to_affine, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j.p, n, p);       // Z = 1: no inversion needed... (generic path)
-    CKR(hash_to_g2_affine_dev(ctx, (const uint8_t*)ctx->in_c.p, (const uint32_t*)ctx->in_d.p, n, ctx->d_dst, (uint32_t)kDstG2Len, q));
+    CKR(hash_to_g2_affine_dev(ctx, ctx->stream, (const uint8_t*)ctx->in_c.p, (const uint32_t*)ctx->in_d.p, n, ctx->d_dst, (uint32_t)kDstG2Len, q));
     CK(cudaMemcpyAsync(q + n, ctx->g2a_sig.p, sizeof(g2_aff), cudaMemcpyDeviceToDevice, ctx->stream));
     LAUNCH(k_set_neg_g1, 1, 1, p + n);
     fp12* res;
@@ -556,29 +586,65 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
     g2_aff* q = (g2_aff*)ctx->g2a.p;
     g1_aff* p = (g1_aff*)ctx->g1a.p;
     if (n > 0) {
-        // 1. signatures: parse + on-curve + subgroup check (M/src/aggregates.rs:274-276)
-        mark(ctx, ST_SIG_CHECK);
-        LAUNCH(k_g2_parse, nblk(n), B3_TPB, d_sigs, n, (g2_aff*)ctx->g2a_sig.p, d_st_sig, (int32_t*)ctx->ok.p, 1, 1);
-        LAUNCH(k_first_bad, nblk(n), B3_TPB, (const int32_t*)ctx->ok.p, n, index_base, d_first_bad);
-        // 2. aggregate public keys
-        mark(ctx, ST_AGGREGATE);
-        if (d_pk_off) CKR(g1_aggregate_dev_impl(ctx, d_pks, d_pk_off, n, total_keys, (g1_jac*)ctx->g1j.p, d_st_key));
-        else LAUNCH(k_g1_parse, nblk(n), B3_TPB, d_pks, n, (g1_jac*)ctx->g1j.p, d_st_key, 1);
-        // 3. P_j = [c_j] apk_j  (M/src/aggregates.rs:293), affine
-        mark(ctx, ST_G1_MUL);
-        LAUNCH(k_g1_mul_u64, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j.p, d_scalars, n, (g1_jac*)ctx->g1j2.p);
-        LAUNCH(k_g1_to_affine, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j2.p, n, p);
-        // 4. H_j = hash_to_curve_g2(msg_j), affine (M/src/aggregates.rs:290,296)
-        mark(ctx, ST_HASH_TO_G2);
-        CKR(hash_to_g2_affine_dev(ctx, d_msgs, d_msg_off, n, ctx->d_dst, (uint32_t)kDstG2Len, q));
-        // 5. S = sum_j [c_j] sig_j (M/src/aggregates.rs:303)
-        mark(ctx, ST_G2_MUL_SUM);
         CKR(ensure(ctx, ctx->g2j, sizeof(g2_jac) * (n + 1)));
-        LAUNCH(k_g2_mul_u64, nblk(n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, d_scalars, n, (g2_jac*)ctx->g2j.p);
+        CKR(ensure(ctx, ctx->g2j_h, sizeof(g2_jac) * (n + 1)));
+        // The four stages below are independent of each other; unless ctx->serial they run concurrently:
+        //   main : parse signatures -> S = sum_j [c_j] sig_j            aux0 : subgroup checks of the parsed signatures
+        //   aux1 : aggregate keys -> P_j = [c_j] apk_j                  aux2 : H_j = hash_to_curve_g2(msg_j)
+        cudaStream_t sm = ctx->stream;
+        cudaStream_t s0 = ctx->serial ? sm : ctx->aux[0], s1 = ctx->serial ? sm : ctx->aux[1], s2 = ctx->serial ? sm : ctx->aux[2];
+        int sp;
+        if (!ctx->serial) {
+            CK(cudaEventRecord(ctx->ev_fork, sm));
+            CK(cudaStreamWaitEvent(s1, ctx->ev_fork, 0));
+            CK(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
+        }
+        // 1. signatures: parse + on-curve (main), subgroup check (M/src/aggregates.rs:274-276) on aux0
+        sp = span_begin(ctx, ST_COPY, sm);
+        LAUNCH_ON(sm, k_g2_parse, nblk(n), B3_TPB, d_sigs, n, (g2_aff*)ctx->g2a_sig.p, d_st_sig, (int32_t*)nullptr, 1, 0);
+        span_end(ctx, sp, sm);
+        if (!ctx->serial) {
+            CK(cudaEventRecord(ctx->ev_fork2, sm));
+            CK(cudaStreamWaitEvent(s0, ctx->ev_fork2, 0));
+        }
+        sp = span_begin(ctx, ST_SIG_CHECK, s0);
+        LAUNCH_ON(s0, k_g2_subgroup, nblk(n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, (const int32_t*)d_st_sig, n, (int32_t*)ctx->ok.p);
+        LAUNCH_ON(s0, k_first_bad, nblk(n), B3_TPB, (const int32_t*)ctx->ok.p, n, index_base, d_first_bad);
+        span_end(ctx, sp, s0);
+        // 2. aggregate public keys; 3. P_j = [c_j] apk_j (M/src/aggregates.rs:293), affine
+        sp = span_begin(ctx, ST_AGGREGATE, s1);
+        if (d_pk_off) {
+            size_t avg = total_keys / n;
+            if (n >= 16384 || avg <= 8) LAUNCH_ON(s1, k_g1_aggregate<4>, nblk(n * 4), B3_TPB, d_pks, d_pk_off, n, (g1_jac*)ctx->g1j.p, d_st_key);
+            else if (n >= 2048 || avg <= 32) LAUNCH_ON(s1, k_g1_aggregate<8>, nblk(n * 8), B3_TPB, d_pks, d_pk_off, n, (g1_jac*)ctx->g1j.p, d_st_key);
+            else LAUNCH_ON(s1, k_g1_aggregate<32>, nblk(n * 32), B3_TPB, d_pks, d_pk_off, n, (g1_jac*)ctx->g1j.p, d_st_key);
+        } else {
+            LAUNCH_ON(s1, k_g1_parse, nblk(n), B3_TPB, d_pks, n, (g1_jac*)ctx->g1j.p, d_st_key, 1);
+        }
+        span_end(ctx, sp, s1);
+        sp = span_begin(ctx, ST_G1_MUL, s1);
+        LAUNCH_ON(s1, k_g1_mul_u64, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j.p, d_scalars, n, (g1_jac*)ctx->g1j2.p);
+        LAUNCH_ON(s1, k_g1_to_affine, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j2.p, n, p);
+        LAUNCH_ON(s1, k_set_neg_g1, 1, 1, p + n);
+        span_end(ctx, sp, s1);
+        // 4. H_j = hash_to_curve_g2(msg_j), affine (M/src/aggregates.rs:290,296)
+        sp = span_begin(ctx, ST_HASH_TO_G2, s2);
+        CKR(hash_to_g2_affine_dev(ctx, s2, d_msgs, d_msg_off, n, ctx->d_dst, (uint32_t)kDstG2Len, q));
+        span_end(ctx, sp, s2);
+        // 5. S = sum_j [c_j] sig_j (M/src/aggregates.rs:303)
+        sp = span_begin(ctx, ST_G2_MUL_SUM, sm);
+        LAUNCH_ON(sm, k_g2_mul_u64, nblk(n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, d_scalars, n, (g2_jac*)ctx->g2j.p);
         g2_jac* s;
         CKR(g2_sum(ctx, (g2_jac*)ctx->g2j.p, (g2_jac*)ctx->g2j2.p, n, &s));
-        LAUNCH(k_g2_to_affine, 1, B3_TPB, (const g2_jac*)s, 1, q + n);
-        LAUNCH(k_set_neg_g1, 1, 1, p + n);
+        LAUNCH_ON(sm, k_g2_to_affine, 1, B3_TPB, (const g2_jac*)s, 1, q + n);
+        span_end(ctx, sp, sm);
+        if (!ctx->serial) {
+            cudaStream_t auxs[3] = {s0, s1, s2};
+            for (int k = 0; k < 3; k++) {
+                CK(cudaEventRecord(ctx->ev_join[k], auxs[k]));
+                CK(cudaStreamWaitEvent(sm, ctx->ev_join[k], 0));
+            }
+        }
     }
     // 6. Miller loops over the n + 1 pairs, product
     CKR(miller_product(ctx, q, p, n ? n + 1 : 0, res));
@@ -672,7 +738,6 @@ extern "C" int b3_verify_multiple_partial_dev(b3_ctx* ctx, const uint8_t* sigs19
                              &perr));
     if (perr) return perr;
     LAUNCH(k_pack_partial, 1, 1, (const fp12*)res, (const long long*)d_fb, (partial_rec*)partial_dev);
-    mark(ctx, ST_END);
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     CKR(sync(ctx));
     mark_collect(ctx);

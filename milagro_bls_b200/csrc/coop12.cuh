@@ -1,0 +1,154 @@
+// Cooperative Fp12 arithmetic: ONE CTA (B3_COOP_THREADS threads) works on Fp12 values held in shared memory.
+//
+// Used where the path is a single long dependent chain of Fp12 operations with nothing else to run beside it:
+// the final exponentiation (A/pair.rs:409-541) and the closing sqr/mul chain of the multi-Miller loop
+// (A/pair.rs:166-178).  An Fp12 product is done schoolbook over the six Fp2 coefficients of the w-power basis
+// (w^6 = xi): 36 Fp2 products = 108 Fp products (Karatsuba inside each Fp2 product), ONE Fp product per thread,
+// then 12 threads assemble the 12 output coordinates.  Latency of an Fp12 multiplication or squaring is therefore
+// about two Fp-multiplication latencies instead of 54 (18 for a cyclotomic squaring) on one thread.
+//
+// Every routine is written as per-thread "phase" functions taking an explicit thread index, with a CTA barrier
+// between phases, so tests/hostsim can replay the phases sequentially on the CPU.
+#pragma once
+#include "pairing.cuh"
+
+#define B3_COOP_THREADS 128
+
+struct coop_ws {
+    fp prod[108];
+};
+
+// w-power k (0..5) -> index of that Fp2 coefficient in the memory order of fp12 (c0.c0,c0.c1,c0.c2,c1.c0,c1.c1,c1.c2)
+B3_FN int coop_slot(int k) { return (k & 1) ? 3 + (k >> 1) : (k >> 1); }
+B3_FN const fp2& coop_coef(const fp12& a, int k) { return reinterpret_cast<const fp2*>(&a)[coop_slot(k)]; }
+B3_FN fp2& coop_coef(fp12& a, int k) { return reinterpret_cast<fp2*>(&a)[coop_slot(k)]; }
+
+// ---- r = a * b --------------------------------------------------------------------------------
+// phase 1: thread tid < 108 computes one of the three Karatsuba products of a_i * b_j
+B3_FN void coop_mul_p1(coop_ws& ws, const fp12& a, const fp12& b, int tid) {
+    if (tid >= 108) return;
+    int pr = tid / 3, k = tid - 3 * pr, i = pr / 6, j = pr - 6 * i;
+    const fp2& x = coop_coef(a, i);
+    const fp2& y = coop_coef(b, j);
+    fp u, v;
+    if (k == 0) { u = x.c0; v = y.c0; }
+    else if (k == 1) { u = x.c1; v = y.c1; }
+    else { fp_add(u, x.c0, x.c1); fp_add(v, y.c0, y.c1); }
+    fp_mul(ws.prod[tid], u, v);
+}
+// phase 2: thread tid < 12 assembles one Fp coordinate of r.  With (p0, p1, p2) the products of (a_i, b_j):
+//   a_i b_j = t0 + t1 i,  t0 = p0 - p1,  t1 = p2 - p0 - p1;   xi (t0 + t1 i) = (2 p0 - p2) + (p2 - 2 p1) i
+B3_FN void coop_mul_p2(fp12& r, const coop_ws& ws, int tid) {
+    if (tid >= 12) return;
+    int k = tid >> 1, comp = tid & 1;
+    fp acc = FP_NIL;
+    for (int i = 0; i < 6; i++) {
+        int j = k - i;
+        bool wrap = j < 0;
+        if (wrap) j += 6;
+        const fp* p = &ws.prod[(i * 6 + j) * 3];
+        fp t;
+        if (!comp) {
+            if (!wrap) fp_sub(t, p[0], p[1]);
+            else { fp_dbl(t, p[0]); fp_sub(t, t, p[2]); }
+        } else {
+            if (!wrap) { fp_sub(t, p[2], p[0]); fp_sub(t, t, p[1]); }
+            else { fp_dbl(t, p[1]); fp_sub(t, p[2], t); }
+        }
+        fp_add(acc, acc, t);
+    }
+    fp2& o = coop_coef(r, k);
+    if (comp) o.c1 = acc; else o.c0 = acc;
+}
+// ---- r = conj(a) (w -> -w): odd w-powers negated -----------------------------------------------------------
+B3_FN void coop_conj_p(fp12& r, const fp12& a, int tid) {
+    if (tid >= 6) return;
+    const fp2& x = coop_coef(a, tid);
+    fp2 t;
+    if (tid & 1) fp2_neg(t, x); else t = x;
+    coop_coef(r, tid) = t;
+}
+// ---- Frobenius maps, one coefficient per thread (n = 1, 2, 3) ------------------------------------------------
+B3_FN void coop_frob_p(fp12& r, const fp12& a, int n, int tid) {
+    if (tid >= 6) return;
+    fp2 t = coop_coef(a, tid), o;
+    if (n == 2) {
+        if (tid == 0) o = t; else fp2_mul_fp(o, t, FROB_GAMMA2[tid]);
+    } else {
+        fp2_conj(t, t);
+        if (tid == 0) o = t; else fp2_mul(o, t, n == 1 ? FROB_GAMMA1[tid] : FROB_GAMMA3[tid]);
+    }
+    coop_coef(r, tid) = o;
+}
+B3_FN void coop_copy_p(fp12& r, const fp12& a, int tid) {
+    if (tid >= 12) return;
+    reinterpret_cast<fp*>(&r)[tid] = reinterpret_cast<const fp*>(&a)[tid];
+}
+
+// A phase: every thread of the CTA runs `stmt` with its index `tid`, then the CTA synchronises.  The host build
+// (tests/hostsim) replays the threads of a phase one after another.
+#if defined(B3_HOSTSIM)
+#define COOP_PHASE(stmt) do { for (int tid = 0; tid < B3_COOP_THREADS; tid++) { stmt; } } while (0)
+#define COOP_FN static
+#else
+#define COOP_PHASE(stmt) do { { const int tid = (int)threadIdx.x; stmt; } __syncthreads(); } while (0)
+#define COOP_FN __device__ __noinline__
+#endif
+// r may alias a and/or b: phase 1 reads a, b; phase 2 reads only ws
+COOP_FN void coop_fp12_mul(fp12& r, const fp12& a, const fp12& b, coop_ws& ws) {
+    COOP_PHASE(coop_mul_p1(ws, a, b, tid));
+    COOP_PHASE(coop_mul_p2(r, ws, tid));
+}
+COOP_FN void coop_fp12_conj(fp12& r, const fp12& a) { COOP_PHASE(coop_conj_p(r, a, tid)); }
+COOP_FN void coop_fp12_frob(fp12& r, const fp12& a, int n) { COOP_PHASE(coop_frob_p(r, a, n, tid)); }   // r must not alias a
+COOP_FN void coop_fp12_copy(fp12& r, const fp12& a) { COOP_PHASE(coop_copy_p(r, a, tid)); }
+// r = a^(|x| >> shift) by plain square-and-multiply; r must not alias a
+COOP_FN void coop_fp12_pow_x_abs(fp12& r, const fp12& a, int shift, coop_ws& ws) {
+    const uint64_t x = B3_X_ABS >> shift;
+    coop_fp12_copy(r, a);
+    for (int i = 62 - shift; i >= 0; i--) {
+        coop_fp12_mul(r, r, r, ws);
+        if ((x >> i) & 1) coop_fp12_mul(r, r, a, ws);
+    }
+}
+// r = a^x (x negative): pow(|x|) then conjugate
+COOP_FN void coop_fp12_pow_x(fp12& r, const fp12& a, int shift, coop_ws& ws) {
+    coop_fp12_pow_x_abs(r, a, shift, ws);
+    coop_fp12_conj(r, r);
+}
+
+struct coop_fexp_ws {
+    coop_ws ws;
+    fp12 m, t, y0, y1, y2, y3, rr;
+};
+// Final exponentiation, same chain as final_exp() in pairing.cuh (exponent 3 (p^12 - 1) / r), CTA-cooperative.
+// in: s.m; out: s.rr
+COOP_FN void coop_final_exp(coop_fexp_ws& s) {
+    coop_ws& ws = s.ws;
+    COOP_PHASE(if (tid == 0) fp12_inv(s.t, s.m));
+    coop_fp12_conj(s.rr, s.m);
+    coop_fp12_mul(s.rr, s.rr, s.t, ws);              // m^(p^6 - 1)
+    coop_fp12_frob(s.t, s.rr, 2);
+    coop_fp12_mul(s.rr, s.t, s.rr, ws);              // ^(p^2 + 1)
+    coop_fp12_mul(s.y0, s.rr, s.rr, ws);             // y0 = r^2
+    coop_fp12_pow_x(s.y1, s.y0, 0, ws);              // y1 = y0^x
+    coop_fp12_pow_x(s.y2, s.y1, 1, ws);              // y2 = y1^(x/2)
+    coop_fp12_conj(s.y3, s.rr);
+    coop_fp12_mul(s.y1, s.y1, s.y3, ws);
+    coop_fp12_conj(s.y1, s.y1);
+    coop_fp12_mul(s.y1, s.y1, s.y2, ws);
+    coop_fp12_pow_x(s.y2, s.y1, 0, ws);
+    coop_fp12_pow_x(s.y3, s.y2, 0, ws);
+    coop_fp12_conj(s.y1, s.y1);
+    coop_fp12_mul(s.y3, s.y3, s.y1, ws);
+    coop_fp12_conj(s.y1, s.y1);
+    coop_fp12_frob(s.t, s.y1, 3);                    // t  = frob3(y1)
+    coop_fp12_frob(s.y1, s.y2, 2);                   // y1 = frob2(y2)
+    coop_fp12_mul(s.y1, s.t, s.y1, ws);              // y1 = frob3(y1) * frob2(y2)
+    coop_fp12_pow_x(s.y2, s.y3, 0, ws);
+    coop_fp12_mul(s.y2, s.y2, s.y0, ws);
+    coop_fp12_mul(s.y2, s.y2, s.rr, ws);
+    coop_fp12_mul(s.y1, s.y1, s.y2, ws);
+    coop_fp12_frob(s.y2, s.y3, 1);
+    coop_fp12_mul(s.rr, s.y1, s.y2, ws);
+}

@@ -3,6 +3,7 @@
 #pragma once
 #include "h2c.cuh"
 #include "pairing.cuh"
+#include "coop12.cuh"
 
 #define B3_ERR_AGGREGATE_EMPTY_POINTS_D (-1)
 #define B3_ERR_INVALID_G1_SIZE_D (-6)
@@ -41,6 +42,19 @@ __global__ void __launch_bounds__(B3_TPB) k_g2_parse(const uint8_t* __restrict__
     out[i] = a;
     status[i] = e;
     if (ok) ok[i] = (e == B3_OK) ? good : 0;
+}
+// subgroup_check_g2 on parsed signatures: ok[i] = parsed fine && in G2 (infinity passes)
+__global__ void __launch_bounds__(B3_TPB) k_g2_subgroup(const g2_aff* pts, const int32_t* status, size_t n, int32_t* ok) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int good = 0;
+    if (status[i] == B3_OK) {
+        g2_aff a = pts[i];
+        g2_jac j;
+        pt_from_aff(j, a);
+        good = g2_in_subgroup(j) ? 1 : 0;
+    }
+    ok[i] = good;
 }
 // key_validate on parsed G1 points (not infinity, in G1)
 __global__ void __launch_bounds__(B3_TPB) k_g1_key_validate(const g1_jac* pts, const int32_t* status, size_t n, int32_t* valid) {
@@ -426,11 +440,20 @@ __global__ void k_first_bad(const int32_t* ok, size_t n, long long index_base, l
     if (i >= n) return;
     if (!ok[i]) atomicMin(out, index_base + (long long)i);
 }
-__global__ void k_final_exp(const fp12* in, uint8_t* gt_wire, int32_t* is_one) {
-    fp12 m = *in, r;
-    final_exp(r, m);
-    fp12_to_wire(gt_wire, r);
-    *is_one = fp12_is_one(r) ? 1 : 0;
+// Final exponentiation + is_unity + GT wire bytes: one CTA, cooperative Fp12 arithmetic (coop12.cuh)
+__global__ void __launch_bounds__(B3_COOP_THREADS) k_final_exp(const fp12* in, uint8_t* gt_wire, int32_t* is_one) {
+    __shared__ coop_fexp_ws s;
+    COOP_PHASE(coop_copy_p(s.m, *in, tid));
+    coop_final_exp(s);
+    const int tid = (int)threadIdx.x;
+    if (tid < 12) {                                   // wire order w^0, w^3, w^1, w^4, w^2, w^5, each (re, im)
+        const int order[6] = {0, 3, 1, 4, 2, 5};
+        const fp2& c = coop_coef(s.rr, order[tid >> 1]);
+        fp t;
+        fp_from_mont(t, (tid & 1) ? c.c1 : c.c0);
+        fp_raw_to_be(gt_wire + 48 * tid, t);
+    }
+    if (tid == 0) *is_one = fp12_is_one(s.rr) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------ roofline microbenchmarks

@@ -252,3 +252,37 @@ def test_pairing_gt_bytes_and_verify(hs):
     assert gt.raw == O.f12_to_bytes(O.fexp(O.ate2(sig, O.NEG_G1, H2, pk)))
     # infinity on either side contributes 1
     assert hs.hs_multi_pairing(g2w(None) + g2w(H), g1w(pk) + g1w(None), 2, gt, ctypes.byref(one)) == 0 and one.value == 1
+
+
+# ---- CTA-cooperative Fp12 routines (coop12.cuh), phases replayed sequentially on the host
+SRC_COOP = os.path.join(HERE, "hostsim", "hostsim_coop.cpp")
+LIB_COOP = os.path.join(HERE, "hostsim", "libhostsim_coop.so")
+
+
+@pytest.fixture(scope="module")
+def hc():
+    deps = [SRC_COOP] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    if not os.path.exists(LIB_COOP) or any(os.path.getmtime(d) > os.path.getmtime(LIB_COOP) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-x", "c++", "-shared", "-fPIC", "-o", LIB_COOP, SRC_COOP])
+    return ctypes.CDLL(LIB_COOP)
+
+
+def coop_op(hc, op, a, b=None):
+    out = ctypes.create_string_buffer(576)
+    hc.hc_fp12_op(op, O.f12_to_bytes(a), O.f12_to_bytes(b if b is not None else a), out)
+    return out.raw
+
+
+def test_coop_fp12(hc):
+    for _ in range(3):
+        a, b = rf12(), rf12()
+        assert coop_op(hc, 0, a, b) == O.f12_to_bytes(O.f12_mul(a, b))
+        assert coop_op(hc, 0, a, a) == O.f12_to_bytes(O.f12_sqr(a))
+        assert coop_op(hc, 1, a) == O.f12_to_bytes(O.f12_conj(a))
+        assert coop_op(hc, 2, a) == O.f12_to_bytes(O.f12_frob(a))
+        assert coop_op(hc, 3, a) == O.f12_to_bytes(O.f12_frob(O.f12_frob(a)))
+        assert coop_op(hc, 4, a) == O.f12_to_bytes(O.f12_frob(O.f12_frob(O.f12_frob(a))))
+    a = rf12()
+    assert coop_op(hc, 5, a) == O.f12_to_bytes(O.f12_conj(O.f12_pow(a, O.BNX)))
+    assert coop_op(hc, 6, a) == O.f12_to_bytes(O.f12_conj(O.f12_pow(a, O.BNX >> 1)))
+    assert coop_op(hc, 7, a) == O.f12_to_bytes(O.fexp(a))
