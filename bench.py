@@ -35,7 +35,7 @@ R_ORDER = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
 # algorithmic work per unit: 32x32->64 multiply-accumulates, 300 per Fp multiplication
 MACS_PER_FP_MUL = 300
 FP_MULS = {"g1_aggregate": 1400, "g2_parse_subgroup_check": 1170, "hash_to_g2_affine": 6700, "g1_scalar_mul_affine": 670 + 15,
-           "g2_scalar_mul_sum": 1650, "miller_loop": 4800, "fp12_product_tree": 54, "final_exp": 0}
+           "g2_scalar_mul_sum": 1650, "miller_lines": 1800, "miller_accumulate": 3000, "miller_chain": 0, "final_exp": 0}
 FP_MULS_PER_SET = 16400
 BYTES_PER_SET = KEYS_PER_SET * 96 + 192 + MSG_LEN + 8          # algorithmic HBM bytes read per set
 
@@ -309,7 +309,7 @@ def main():
         peak_imad = eng.imad_peak(wide=False)
         dom = max((k for k in stages if k in FP_MULS and FP_MULS[k] > 0), key=lambda k: stages[k])
         dom_ms = stages[dom]
-        units = n + (1 if dom == "miller_loop" else 0)
+        units = n + (1 if dom.startswith("miller") else 0)
         macs = FP_MULS[dom] * MACS_PER_FP_MUL * units
         achieved = macs / (dom_ms * 1e-3)
         step_ms = ms_res / args.steps

@@ -18,11 +18,11 @@ static const uint8_t kDstG2[] = "BLS_SIG_BLS12381G2_XMD:SHA-256_SSWU_RO_POP_";  
 static const size_t kDstG2Len = 43;
 
 #define B3_MAX_MARKS 24
-#define B3_N_STAGES 10
+#define B3_N_STAGES 11
 // stage ids (b3_ctx_stage_ms / b3_stage_name)
-enum { ST_SIG_CHECK = 0, ST_AGGREGATE, ST_G1_MUL, ST_HASH_TO_G2, ST_G2_MUL_SUM, ST_MILLER, ST_FP12_PRODUCT, ST_FINAL_EXP, ST_COPY, ST_END };
+enum { ST_SIG_CHECK = 0, ST_AGGREGATE, ST_G1_MUL, ST_HASH_TO_G2, ST_G2_MUL_SUM, ST_MILLER, ST_FP12_PRODUCT, ST_FINAL_EXP, ST_COPY, ST_MILLER_LINES, ST_END };
 static const char* kStageNames[B3_N_STAGES] = {"g2_parse_subgroup_check", "g1_aggregate", "g1_scalar_mul_affine", "hash_to_g2_affine",
-                                               "g2_scalar_mul_sum", "miller_loop", "fp12_product_tree", "final_exp", "parse_copies", "end"};
+                                               "g2_scalar_mul_sum", "miller_accumulate", "miller_chain", "final_exp", "parse_copies", "miller_lines", "end"};
 
 struct dev_buf {
     void* p = nullptr;
@@ -47,7 +47,7 @@ struct b3_ctx {
     int serial = 0;
     // scratch (grown on demand, reused across calls)
     dev_buf in_a, in_b, in_c, in_d, in_e, in_f;      // staged host inputs
-    dev_buf g1j, g1j2, g1a, g2a_sig, g2j, g2j2, g2j_h, g2a, f12a, f12b, status, ok, misc, outb;
+    dev_buf g1j, g1j2, g1a, g2a_sig, g2j, g2j2, g2j_h, g2a, f12a, f12b, lines, status, ok, misc, outb;
     uint8_t* d_dst = nullptr;
 };
 
@@ -119,7 +119,7 @@ extern "C" void b3_ctx_destroy(b3_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     dev_buf* bufs[] = {&ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->in_d, &ctx->in_e, &ctx->in_f, &ctx->g1j, &ctx->g1j2, &ctx->g1a,
-                       &ctx->g2a_sig, &ctx->g2j, &ctx->g2j2, &ctx->g2j_h, &ctx->g2a, &ctx->f12a, &ctx->f12b, &ctx->status, &ctx->ok,
+                       &ctx->g2a_sig, &ctx->g2j, &ctx->g2j2, &ctx->g2j_h, &ctx->g2a, &ctx->lines, &ctx->f12a, &ctx->f12b, &ctx->status, &ctx->ok,
                        &ctx->misc, &ctx->outb};
     for (dev_buf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_dst) cudaFree(ctx->d_dst);
@@ -205,25 +205,41 @@ static int g2_sum(b3_ctx* ctx, g2_jac* a, g2_jac* b, size_t n, g2_jac** res) {
     *res = src;
     return B3_OK;
 }
-// Miller loops over n_pairs (q[i], p[i]) -> product left in *res
+// Miller loops over n_pairs (q[i], p[i]) -> product left in *res.  Split multi-Miller loop (pairing.cuh):
+// point chains -> lines in HBM (68 x n x 288 B), per-slot accumulation over all pairs, one cooperative closing chain.
 static int miller_product(b3_ctx* ctx, const g2_aff* q, const g1_aff* p, size_t n_pairs, fp12** res) {
-    CKR(ensure(ctx, ctx->f12a, sizeof(fp12) * (n_pairs + 1)));
-    CKR(ensure(ctx, ctx->f12b, sizeof(fp12) * (n_pairs / 2 + 2)));
-    fp12* fa = (fp12*)ctx->f12a.p;
+    size_t chunks = (n_pairs + 1024) / 2048;              // ~16 pairs per accumulating thread
+    if (chunks < 1) chunks = 1;
+    if (chunks > 64) chunks = 64;
+    unsigned K = (unsigned)((n_pairs + chunks * B3_TPB - 1) / (chunks * B3_TPB));
+    CKR(ensure(ctx, ctx->f12a, sizeof(fp12) * (B3_MILLER_SLOTS * (chunks + 1) + 2)));
+    fp12* partial = (fp12*)ctx->f12a.p;
+    fp12* slotvals = partial + B3_MILLER_SLOTS * chunks;
+    fp12* out = slotvals + B3_MILLER_SLOTS;
+    *res = out;
     if (n_pairs == 0) {
-        LAUNCH(k_fp12_set_one, 1, 1, fa);
-        *res = fa;
+        LAUNCH(k_fp12_set_one, 1, 1, out);
         return B3_OK;
     }
+    CKR(ensure(ctx, ctx->lines, sizeof(fp2) * 3 * B3_MILLER_SLOTS * n_pairs));
+    fp2* lines = (fp2*)ctx->lines.p;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-    int sp = span_begin(ctx, ST_MILLER, ctx->stream);
-    LAUNCH(k_miller, nblk(n_pairs), B3_TPB, q, p, n_pairs, fa);
+    int sp = span_begin(ctx, ST_MILLER_LINES, ctx->stream);
+    LAUNCH(k_miller_lines, nblk(n_pairs), B3_TPB, q, n_pairs, lines);
+    span_end(ctx, sp, ctx->stream);
+    sp = span_begin(ctx, ST_MILLER, ctx->stream);
+    LAUNCH(k_miller_accum, dim3((unsigned)chunks, B3_MILLER_SLOTS), B3_TPB, (const fp2*)lines, q, p, n_pairs, K, partial);
     span_end(ctx, sp, ctx->stream);
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     sp = span_begin(ctx, ST_FP12_PRODUCT, ctx->stream);
-    int rc = fp12_product(ctx, fa, (fp12*)ctx->f12b.p, n_pairs, res);
+    if (chunks > 1) {
+        LAUNCH(k_miller_slots, B3_MILLER_SLOTS, B3_COOP_THREADS, (const fp12*)partial, (unsigned)chunks, slotvals);
+        LAUNCH(k_miller_chain, 1, B3_COOP_THREADS, (const fp12*)slotvals, 1u, out);
+    } else {
+        LAUNCH(k_miller_chain, 1, B3_COOP_THREADS, (const fp12*)partial, 1u, out);
+    }
     span_end(ctx, sp, ctx->stream);
-    return rc;
+    return B3_OK;
 }
 // final exponentiation of *m -> accept / gt on the host
 static int finish(b3_ctx* ctx, const fp12* m, int* accept, uint8_t* gt576) {

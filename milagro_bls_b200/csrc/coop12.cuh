@@ -117,6 +117,22 @@ COOP_FN void coop_fp12_pow_x(fp12& r, const fp12& a, int shift, coop_ws& ws) {
     coop_fp12_conj(r, r);
 }
 
+// Closing chain of the split Miller loop (pairing.cuh): slots[s] = product over all pairs of the lines of slot s.
+//   f = 1; for it = 0..62: f = f^2 * slots[it] [* slots[63 + k] on the addition steps]; f = conj(f)
+COOP_FN void coop_miller_chain(fp12& f, const fp12* slots, coop_ws& ws) {
+    const uint64_t x = B3_X_ABS;
+    int a = B3_MILLER_DBL_SLOTS;
+    coop_fp12_copy(f, slots[0]);
+    for (int it = 0; it < B3_MILLER_DBL_SLOTS; it++) {
+        if (it) {
+            coop_fp12_mul(f, f, f, ws);
+            coop_fp12_mul(f, f, slots[it], ws);
+        }
+        if ((x >> (62 - it)) & 1) coop_fp12_mul(f, f, slots[a++], ws);
+    }
+    coop_fp12_conj(f, f);
+}
+
 struct coop_fexp_ws {
     coop_ws ws;
     fp12 m, t, y0, y1, y2, y3, rr;

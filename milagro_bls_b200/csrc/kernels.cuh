@@ -407,16 +407,97 @@ __global__ void __launch_bounds__(B3_TPB) k_hash_to_g2(const uint8_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------ pairing
-// one Miller loop per thread
-__global__ void __launch_bounds__(B3_TPB) k_miller(const g2_aff* q, const g1_aff* p, size_t n, fp12* out) {
+// ---- split multi-Miller loop (pairing.cuh: "split Miller loop") ---------------------------------------------------
+// 1. point chain of every pair -> unscaled lines, lines[(slot * n + pair) * 3 + {0,1,2}] = (u0, l3, u5)
+__global__ void __launch_bounds__(B3_TPB) k_miller_lines(const g2_aff* __restrict__ q, size_t n, fp2* __restrict__ lines) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g2_aff Q = q[i];
-    g1_aff P = p[i];
-    fp12 f;
-    miller_loop_pair(f, Q, P);
-    out[i] = f;
+    if (Q.inf) return;                         // never read: the accumulate kernel skips pairs with an infinite member
+    miller_pt t;
+    t.x = Q.x; t.y = Q.y; fp2_one(t.z);
+    const uint64_t x = B3_X_ABS;
+    int a = B3_MILLER_DBL_SLOTS;
+    fp2 u0, l3, u5;
+    for (int it = 0; it < B3_MILLER_DBL_SLOTS; it++) {
+        miller_dbl_step_u(t, u0, l3, u5);
+        fp2* o = lines + ((size_t)it * n + i) * 3;
+        o[0] = u0; o[1] = l3; o[2] = u5;
+        if ((x >> (62 - it)) & 1) {
+            miller_add_step_u(t, u0, l3, u5, Q.x, Q.y);
+            o = lines + ((size_t)a * n + i) * 3;
+            o[0] = u0; o[1] = l3; o[2] = u5;
+            a++;
+        }
+    }
 }
+// 2. slot accumulators.  grid = (chunks, B3_MILLER_SLOTS), block = 128: thread g of slot s folds the lines of pairs
+//    [g K, (g+1) K) into a dense Fp12 (sparse multiplications), the warp reduces by a shuffle tree of Fp12 products,
+//    the four warp results are multiplied CTA-cooperatively; partial[s * chunks + chunk] = product of the CTA's lines.
+__global__ void __launch_bounds__(B3_TPB) k_miller_accum(const fp2* __restrict__ lines, const g2_aff* __restrict__ q,
+                                                         const g1_aff* __restrict__ p, size_t n, unsigned K, fp12* partial) {
+    __shared__ fp12 wres[B3_TPB / 32];
+    __shared__ coop_ws ws;
+    const unsigned slot = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+    const size_t g = (size_t)chunk * B3_TPB + threadIdx.x;
+    size_t b = g * K, e = b + K;
+    if (e > n) e = n;
+    fp12 acc;
+    bool have = false;
+    for (size_t j = b; j < e; j++) {
+        if (q[j].inf || p[j].inf) continue;
+        const fp2* l = lines + ((size_t)slot * n + j) * 3;
+        fp xp = p[j].x, nyp;
+        fp_neg(nyp, p[j].y);
+        fp2 l0, l3 = l[1], l5;
+        fp2_mul_fp(l0, l[0], nyp);
+        fp2_mul_fp(l5, l[2], xp);
+        if (have) fp12_mul_by_line(acc, l0, l3, l5);
+        else { fp12_from_line(acc, l0, l3, l5); have = true; }
+    }
+    if (!have) fp12_one(acc);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        fp12 o;
+        shfl_down_struct(o, acc, d, 32);
+        if (lane < d) fp12_mul(acc, acc, o);
+    }
+    if (lane == 0) wres[warp] = acc;
+    __syncthreads();
+    coop_fp12_mul(wres[0], wres[0], wres[1], ws);
+    coop_fp12_mul(wres[2], wres[2], wres[3], ws);
+    coop_fp12_mul(wres[0], wres[0], wres[2], ws);
+    coop_copy_p(partial[(size_t)slot * chunks + chunk], wres[0], (int)threadIdx.x);
+}
+// 2b. one CTA per slot: slot value = product of that slot's per-chunk partials (only launched when chunks > 1)
+__global__ void __launch_bounds__(B3_COOP_THREADS) k_miller_slots(const fp12* partial, unsigned chunks, fp12* slotvals) {
+    __shared__ fp12 acc, tmp;
+    __shared__ coop_ws ws;
+    const unsigned s = blockIdx.x;
+    COOP_PHASE(coop_copy_p(acc, partial[(size_t)s * chunks], tid));
+    for (unsigned c = 1; c < chunks; c++) {
+        COOP_PHASE(coop_copy_p(tmp, partial[(size_t)s * chunks + c], tid));
+        coop_fp12_mul(acc, acc, tmp, ws);
+    }
+    coop_copy_p(slotvals[s], acc, (int)threadIdx.x);
+}
+// 3. one CTA: slot values = products of the per-chunk partials, then the closing sqr/mul chain -> *out
+__global__ void __launch_bounds__(B3_COOP_THREADS) k_miller_chain(const fp12* partial, unsigned chunks, fp12* out) {
+    __shared__ fp12 slots[B3_MILLER_SLOTS];
+    __shared__ fp12 f, tmp;
+    __shared__ coop_ws ws;
+    for (unsigned s = 0; s < B3_MILLER_SLOTS; s++) {
+        COOP_PHASE(coop_copy_p(slots[s], partial[(size_t)s * chunks], tid));
+        for (unsigned c = 1; c < chunks; c++) {
+            COOP_PHASE(coop_copy_p(tmp, partial[(size_t)s * chunks + c], tid));
+            coop_fp12_mul(slots[s], slots[s], tmp, ws);
+        }
+    }
+    coop_miller_chain(f, slots, ws);
+    coop_copy_p(*out, f, (int)threadIdx.x);
+}
+
 // pairwise product tree level: out[i] = in[2i] * in[2i+1]
 __global__ void __launch_bounds__(B3_TPB) k_fp12_mul_pairs(const fp12* in, size_t n, fp12* out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -84,6 +84,79 @@ B3_FN_NOINLINE void miller_add_step(miller_pt& t, fp2& l0, fp2& l3, fp2& l5, con
     fp2_mul(t.z, t.z, e);
 }
 
+// ---- split Miller loop (multi-pairing with per-step accumulators, the shape of A/pair.rs:156-238) -----------------
+// The point chain T -> 2T (-> T + Q) of a pair depends only on Q, and the lines it produces are independent of the
+// accumulator f.  So the loop is split in three data-parallel pieces (kernels.cuh):
+//   1. per pair: run the point chain and emit the B3_MILLER_SLOTS lines WITHOUT their P-dependent factors;
+//   2. per (slot, pair): scale the line by (xP, -yP) and multiply it into the slot's accumulator  A_s = prod_pairs l_s
+//      -- every (slot, pair) is independent, and no per-pair Fp12 squarings are needed;
+//   3. once: f = 1; for it = 0..62: f = f^2 * A_it [* A_(63 + k) on the 5 addition steps]; conj.
+// Slot it (0..62) holds the doubling line of loop index i = 62 - it; slots 63..67 hold the addition lines in loop order.
+#define B3_MILLER_DBL_SLOTS 63
+#define B3_MILLER_SLOTS 68
+// Unscaled doubling step.  Full line: l0 = u0 * (-yP),  l3,  l5 = u5 * xP   with u0 = xi (2YZ), u5 = 3 X^2.
+B3_FN_NOINLINE void miller_dbl_step_u(miller_pt& t, fp2& u0, fp2& l3, fp2& u5) {
+    fp2 a, b, c, e, f, g, h, j, e2, u;
+    fp2_mul(a, t.x, t.y);
+    fp2_half(a, a);                 // A = XY/2
+    fp2_sqr(b, t.y);                // B = Y^2
+    fp2_sqr(c, t.z);                // C = Z^2
+    fp2_mul3(u, c);
+    f_mul_b(e, u);                  // E = 3 b' C
+    fp2_mul3(f, e);                 // F = 3E
+    fp2_add(g, b, f);
+    fp2_half(g, g);                 // G = (B+F)/2
+    fp2_add(h, t.y, t.z);
+    fp2_sqr(h, h);
+    fp2_add(u, b, c);
+    fp2_sub(h, h, u);               // H = 2YZ
+    fp2_sqr(j, t.x);                // J = X^2
+    fp2_sqr(e2, e);
+    fp2_sub(l3, e, b);
+    fp2_mul3(u5, j);
+    fp2_mul_xi(u0, h);
+    fp2_sub(u, b, f);
+    fp2_mul(t.x, a, u);             // X3 = A (B - F)
+    fp2_sqr(g, g);
+    fp2_mul3(u, e2);
+    fp2_sub(t.y, g, u);             // Y3 = G^2 - 3 E^2
+    fp2_mul(t.z, b, h);             // Z3 = B H
+}
+// Unscaled addition step, signs arranged so that the same factors (-yP, xP) apply as for a doubling line:
+//   l0 = u0 * (-yP), l3, l5 = u5 * xP   with u0 = -xi lambda, u5 = -theta.
+B3_FN_NOINLINE void miller_add_step_u(miller_pt& t, fp2& u0, fp2& l3, fp2& u5, const fp2& xq, const fp2& yq) {
+    fp2 theta, lambda, c, d, e, f, g, h, u;
+    fp2_mul(u, yq, t.z);
+    fp2_sub(theta, t.y, u);
+    fp2_mul(u, xq, t.z);
+    fp2_sub(lambda, t.x, u);
+    fp2_sqr(c, theta);
+    fp2_sqr(d, lambda);
+    fp2_mul(e, lambda, d);
+    fp2_mul(f, t.z, c);
+    fp2_mul(g, t.x, d);
+    fp2_add(h, e, f);
+    fp2_sub(h, h, g);
+    fp2_sub(h, h, g);               // H = E + F - 2G
+    fp2_mul(l3, theta, xq);
+    fp2_mul(u, lambda, yq);
+    fp2_sub(l3, l3, u);
+    fp2_neg(u5, theta);
+    fp2_mul_xi(u, lambda);
+    fp2_neg(u0, u);
+    fp2_mul(t.x, lambda, h);
+    fp2_sub(u, g, h);
+    fp2_mul(u, theta, u);
+    fp2_mul(g, e, t.y);
+    fp2_sub(t.y, u, g);
+    fp2_mul(t.z, t.z, e);
+}
+// dense Fp12 value of a line  l0 + l3 w^3 + l5 w^5
+B3_FN void fp12_from_line(fp12& f, const fp2& l0, const fp2& l3, const fp2& l5) {
+    f.c0.c0 = l0; fp2_zero(f.c0.c1); fp2_zero(f.c0.c2);
+    fp2_zero(f.c1.c0); f.c1.c1 = l3; f.c1.c2 = l5;
+}
+
 // Miller loop of one pair (Q in G2 affine, P in G1 affine), multiplied INTO f (f <- f^(2^63..) is NOT shared
 // here: this routine runs the whole loop on its own accumulator and returns conj(f_{|x|,Q}(P))).
 // Pairs with an infinite member contribute 1.

@@ -31,4 +31,38 @@ void hc_fp12_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     }
     fp12_to_wire(out, s.rr);
 }
+
+// Split multi-Miller loop replayed on the host: lines per pair (miller_*_step_u), per-slot accumulation with the
+// (xP, -yP) scaling, cooperative closing chain, cooperative final exponentiation -> GT bytes.
+int hc_multi_pairing_split(const uint8_t* q192s, const uint8_t* p96s, int n, uint8_t* gt576) {
+    static fp12 slots[B3_MILLER_SLOTS];
+    static coop_fexp_ws s;
+    for (int k = 0; k < B3_MILLER_SLOTS; k++) fp12_one(slots[k]);
+    for (int i = 0; i < n; i++) {
+        g2_aff Q; g1_aff P; int e;
+        if ((e = g2_aff_from_wire(Q, q192s + 192 * i))) return e;
+        if ((e = g1_aff_from_wire(P, p96s + 96 * i))) return e;
+        if (Q.inf || P.inf) continue;
+        miller_pt t; t.x = Q.x; t.y = Q.y; fp2_one(t.z);
+        fp nyp; fp_neg(nyp, P.y);
+        int a = B3_MILLER_DBL_SLOTS;
+        for (int it = 0; it < B3_MILLER_DBL_SLOTS; it++) {
+            fp2 u0, l3, u5, l0, l5;
+            miller_dbl_step_u(t, u0, l3, u5);
+            fp2_mul_fp(l0, u0, nyp); fp2_mul_fp(l5, u5, P.x);
+            fp12_mul_by_line(slots[it], l0, l3, l5);
+            if ((B3_X_ABS >> (62 - it)) & 1) {
+                miller_add_step_u(t, u0, l3, u5, Q.x, Q.y);
+                fp2_mul_fp(l0, u0, nyp); fp2_mul_fp(l5, u5, P.x);
+                fp12 d; fp12_from_line(d, l0, l3, l5);
+                fp12_mul(slots[a], slots[a], d);
+                a++;
+            }
+        }
+    }
+    coop_miller_chain(s.m, slots, s.ws);
+    coop_final_exp(s);
+    fp12_to_wire(gt576, s.rr);
+    return 0;
+}
 }

@@ -286,3 +286,18 @@ def test_coop_fp12(hc):
     assert coop_op(hc, 5, a) == O.f12_to_bytes(O.f12_conj(O.f12_pow(a, O.BNX)))
     assert coop_op(hc, 6, a) == O.f12_to_bytes(O.f12_conj(O.f12_pow(a, O.BNX >> 1)))
     assert coop_op(hc, 7, a) == O.f12_to_bytes(O.fexp(a))
+
+
+def test_split_miller_loop(hc):
+    gt = ctypes.create_string_buffer(576)
+    assert hc.hc_multi_pairing_split(g2w(O.G2_GEN), g1w(O.G1_GEN), 1, gt) == 0
+    assert gt.raw == O.f12_to_bytes(O.fexp(O.ate2(O.G2_GEN, O.G1_GEN, None, None)))
+    sk, msg = 0x1234567890abcdef, b"cats"
+    pk, H = O.sk_to_pk(sk), O.hash_to_curve_g2(msg)
+    sig = O.g2_mul(H, sk)
+    ps = g1w(O.NEG_G1) + g1w(pk)
+    assert hc.hc_multi_pairing_split(g2w(sig) + g2w(H), ps, 2, gt) == 0 and gt.raw == O.f12_to_bytes(O.F12_ONE)
+    H2 = O.hash_to_curve_g2(b"dogs")
+    assert hc.hc_multi_pairing_split(g2w(sig) + g2w(H2), ps, 2, gt) == 0
+    assert gt.raw == O.f12_to_bytes(O.fexp(O.ate2(sig, O.NEG_G1, H2, pk)))
+    assert hc.hc_multi_pairing_split(g2w(None) + g2w(H), g1w(pk) + g1w(None), 2, gt) == 0 and gt.raw == O.f12_to_bytes(O.F12_ONE)
