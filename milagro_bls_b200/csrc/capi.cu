@@ -198,7 +198,7 @@ static int g2_sum(b3_ctx* ctx, g2_jac* a, g2_jac* b, size_t n, g2_jac** res) {
     g2_jac *src = a, *dst = b;
     while (n > 1) {
         size_t m = (n + 1) / 2;
-        LAUNCH(k_g2_add_pairs, nblk(m), B3_TPB, src, n, dst);
+        LAUNCH(k_g2_add_pairs, nblk(2 * m), B3_TPB, src, n, dst);
         g2_jac* t = src; src = dst; dst = t;
         n = m;
     }
@@ -225,7 +225,7 @@ static int miller_product(b3_ctx* ctx, const g2_aff* q, const g1_aff* p, size_t 
     fp2* lines = (fp2*)ctx->lines.p;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     int sp = span_begin(ctx, ST_MILLER_LINES, ctx->stream);
-    LAUNCH(k_miller_lines, nblk(n_pairs), B3_TPB, q, n_pairs, lines);
+    LAUNCH(k_miller_lines, nblk(2 * n_pairs), B3_TPB, q, n_pairs, lines);
     span_end(ctx, sp, ctx->stream);
     sp = span_begin(ctx, ST_MILLER, ctx->stream);
     LAUNCH(k_miller_accum, dim3((unsigned)chunks, B3_MILLER_SLOTS), B3_TPB, (const fp2*)lines, q, p, n_pairs, K, partial);
@@ -353,7 +353,8 @@ extern "C" int b3_g2_subgroup_check(b3_ctx* ctx, const uint8_t* in192, size_t n,
     CKR(ensure(ctx, ctx->g2a_sig, sizeof(g2_aff) * n));
     CKR(ensure(ctx, ctx->status, 4 * n));
     CKR(ensure(ctx, ctx->ok, 4 * n));
-    LAUNCH(k_g2_parse, nblk(n), B3_TPB, (const uint8_t*)ctx->in_a.p, n, (g2_aff*)ctx->g2a_sig.p, (int32_t*)ctx->status.p, (int32_t*)ctx->ok.p, 1, 1);
+    LAUNCH(k_g2_parse, nblk(n), B3_TPB, (const uint8_t*)ctx->in_a.p, n, (g2_aff*)ctx->g2a_sig.p, (int32_t*)ctx->status.p, 1);
+    LAUNCH(k_g2_subgroup, nblk(2 * n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, (const int32_t*)ctx->status.p, n, (int32_t*)ctx->ok.p);
     CKR(d2h(ctx, status, ctx->status.p, 4 * n));
     CKR(d2h(ctx, ok, ctx->ok.p, 4 * n));
     return sync(ctx);
@@ -424,7 +425,7 @@ static int stage_dst(b3_ctx* ctx, const uint8_t* dst, size_t dst_len, const uint
 static int hash_to_g2_affine_dev(b3_ctx* ctx, cudaStream_t strm, const uint8_t* d_msgs, const uint32_t* d_off, size_t n, const uint8_t* d_dst,
                                  uint32_t dst_len, g2_aff* d_out) {
     CKR(ensure(ctx, ctx->g2j_h, sizeof(g2_jac) * n));
-    LAUNCH_ON(strm, k_hash_to_g2, nblk(n), B3_TPB, d_msgs, d_off, n, d_dst, dst_len, (g2_jac*)ctx->g2j_h.p);
+    LAUNCH_ON(strm, k_hash_to_g2, nblk(2 * n), B3_TPB, d_msgs, d_off, n, d_dst, dst_len, (g2_jac*)ctx->g2j_h.p);
     LAUNCH_ON(strm, k_g2_to_affine, nblk(n), B3_TPB, (const g2_jac*)ctx->g2j_h.p, n, d_out);
     return B3_OK;
 }
@@ -500,7 +501,8 @@ static int parse_sig(b3_ctx* ctx, const uint8_t* sig192) {
     CKR(ensure(ctx, ctx->g2a_sig, sizeof(g2_aff)));
     CKR(ensure(ctx, ctx->status, 4 * 4));
     CKR(ensure(ctx, ctx->ok, 4 * 4));
-    LAUNCH(k_g2_parse, 1, B3_TPB, (const uint8_t*)ctx->in_a.p, 1, (g2_aff*)ctx->g2a_sig.p, (int32_t*)ctx->status.p, (int32_t*)ctx->ok.p, 1, 1);
+    LAUNCH(k_g2_parse, 1, B3_TPB, (const uint8_t*)ctx->in_a.p, 1, (g2_aff*)ctx->g2a_sig.p, (int32_t*)ctx->status.p, 1);
+    LAUNCH(k_g2_subgroup, 1, B3_TPB, (const g2_aff*)ctx->g2a_sig.p, (const int32_t*)ctx->status.p, 1, (int32_t*)ctx->ok.p);
     return first_status(ctx, (const int32_t*)ctx->status.p, 1);
 }
 extern "C" int b3_fast_aggregate_verify(b3_ctx* ctx, const uint8_t sig192[192], const uint8_t* pks96, size_t n_pks, const uint8_t* msg,
@@ -617,14 +619,14 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
         }
         // 1. signatures: parse + on-curve (main), subgroup check (M/src/aggregates.rs:274-276) on aux0
         sp = span_begin(ctx, ST_COPY, sm);
-        LAUNCH_ON(sm, k_g2_parse, nblk(n), B3_TPB, d_sigs, n, (g2_aff*)ctx->g2a_sig.p, d_st_sig, (int32_t*)nullptr, 1, 0);
+        LAUNCH_ON(sm, k_g2_parse, nblk(n), B3_TPB, d_sigs, n, (g2_aff*)ctx->g2a_sig.p, d_st_sig, 1);
         span_end(ctx, sp, sm);
         if (!ctx->serial) {
             CK(cudaEventRecord(ctx->ev_fork2, sm));
             CK(cudaStreamWaitEvent(s0, ctx->ev_fork2, 0));
         }
         sp = span_begin(ctx, ST_SIG_CHECK, s0);
-        LAUNCH_ON(s0, k_g2_subgroup, nblk(n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, (const int32_t*)d_st_sig, n, (int32_t*)ctx->ok.p);
+        LAUNCH_ON(s0, k_g2_subgroup, nblk(2 * n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, (const int32_t*)d_st_sig, n, (int32_t*)ctx->ok.p);
         LAUNCH_ON(s0, k_first_bad, nblk(n), B3_TPB, (const int32_t*)ctx->ok.p, n, index_base, d_first_bad);
         span_end(ctx, sp, s0);
         // 2. aggregate public keys; 3. P_j = [c_j] apk_j (M/src/aggregates.rs:293), affine
@@ -649,7 +651,7 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
         span_end(ctx, sp, s2);
         // 5. S = sum_j [c_j] sig_j (M/src/aggregates.rs:303)
         sp = span_begin(ctx, ST_G2_MUL_SUM, sm);
-        LAUNCH_ON(sm, k_g2_mul_u64, nblk(n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, d_scalars, n, (g2_jac*)ctx->g2j.p);
+        LAUNCH_ON(sm, k_g2_mul_u64, nblk(2 * n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, d_scalars, n, (g2_jac*)ctx->g2j.p);
         g2_jac* s;
         CKR(g2_sum(ctx, (g2_jac*)ctx->g2j.p, (g2_jac*)ctx->g2j2.p, n, &s));
         LAUNCH_ON(sm, k_g2_to_affine, 1, B3_TPB, (const g2_jac*)s, 1, q + n);

@@ -264,15 +264,21 @@ B3_FN_NOINLINE void pt_mul_u256_aff(jac<F>& r, const aff<F>& p, const uint32_t* 
 }
 
 // ---- endomorphisms ------------------------------------------------------------------------------
+// (templates over the Fp2 representation F2: fp2 = one thread per value, fp2h = lane pairs, see fp2h.cuh)
+B3_FN void f2_const(fp2& r, const fp2& c) { r = c; }
 // psi on G2 (untwist-Frobenius-twist), Jacobian: (conj X * cx, conj Y * cy, conj Z)
 //   reference: A/ecp2.rs:538-548 with X = 1/FROB (A/ecp2.rs:785-789)
-B3_FN_NOINLINE void g2_psi(g2_jac& r, const g2_jac& p) {
-    fp2 t;
-    fp2_conj(t, p.x); fp2_mul(r.x, t, PSI_CX);
-    fp2_conj(t, p.y); fp2_mul(r.y, t, PSI_CY);
+template <class F2>
+B3_FN_NOINLINE void g2_psi(jac<F2>& r, const jac<F2>& p) {
+    F2 t, c;
+    f2_const(c, PSI_CX);
+    fp2_conj(t, p.x); fp2_mul(r.x, t, c);
+    f2_const(c, PSI_CY);
+    fp2_conj(t, p.y); fp2_mul(r.y, t, c);
     fp2_conj(r.z, p.z);
 }
-B3_FN void g2_psi2(g2_jac& r, const g2_jac& p) {
+template <class F2>
+B3_FN void g2_psi2(jac<F2>& r, const jac<F2>& p) {
     fp2_mul_fp(r.x, p.x, PSI2_CX);
     fp2_mul_fp(r.y, p.y, PSI2_CY);
     r.z = p.z;
@@ -283,9 +289,10 @@ B3_FN void g1_phi(g1_jac& r, const g1_jac& p) { fp_mul(r.x, p.x, FP_BETA); r.y =
 // Subgroup membership.  The reference tests [r]P == O through its GLV/GS ladders
 // (A/bls381/core.rs:116-127 -> A/pair.rs:625-693); any exact membership test gives the same answer on
 // every on-curve input.  G2: psi(P) == [x]P = -[|x|]P.  G1: phi(P) == [-x^2]P.
-B3_FN_NOINLINE bool g2_in_subgroup(const g2_jac& p) {
+template <class F2>
+B3_FN_NOINLINE bool g2_in_subgroup(const jac<F2>& p) {
     if (pt_is_inf(p)) return true;
-    g2_jac xp, ps;
+    jac<F2> xp, ps;
     pt_mul_u64(xp, p, B3_X_ABS);
     pt_neg(xp, xp);
     g2_psi(ps, p);
@@ -302,8 +309,9 @@ B3_FN_NOINLINE bool g1_in_subgroup(const g1_jac& p) {
 }
 
 // Budroni-Pintore cofactor clearing: [x^2 - x - 1]P + [x - 1]psi(P) + psi^2(2P)   (A/ecp2.rs:784-805)
-B3_FN_NOINLINE void g2_clear_cofactor(g2_jac& r, const g2_jac& p) {
-    g2_jac xp, x2p, t, np;
+template <class F2>
+B3_FN_NOINLINE void g2_clear_cofactor(jac<F2>& r, const jac<F2>& p) {
+    jac<F2> xp, x2p, t, np;
     pt_mul_u64(xp, p, B3_X_ABS);            // |x| P
     pt_mul_u64(x2p, xp, B3_X_ABS);          // x^2 P
     pt_neg(xp, xp);                         // x P   (x negative)

@@ -235,8 +235,51 @@ B3_FN void fp_mul_inl(fp& r, const fp& a, const fp& b) {
     fp_final_sub(r, even);
 }
 
-B3_FN_NOINLINE void fp_mul(fp& r, const fp& a, const fp& b) { fp_mul_inl(r, a, b); }
-B3_FN_NOINLINE void fp_sqr(fp& r, const fp& a) { fp_mul_inl(r, a, a); }
+// Dual product with ONE reduction:  r = (a1*b1 + a2*b2) / 2^384 mod p      (a1, a2, b1, b2 < p)
+// 2 x 144 + 156 multiply-accumulates instead of 2 x 300.  The running value stays below 3p(1 + 2^-32) < 2^383, and the
+// result below p(1 + 2p/2^384) < 2p, so the accumulator shapes and the single final subtraction of fp_mul_inl carry over.
+B3_FN void b3_mont_row2(uint32_t* even, uint32_t* odd, const uint32_t* a1, uint32_t b1i, const uint32_t* a2, uint32_t b2i, bool first) {
+    if (first) {
+        b3_mul_row(odd, a1 + 1, b1i);
+        b3_mul_row(even, a1, b1i);
+    } else {
+        even[0] = add_cc(even[0], odd[1]);
+        b3_mad_row_shift(odd, a1 + 1, b1i);
+        b3_mad_row(even, a1, b1i);
+        odd[11] = addc(odd[11], 0);
+    }
+    b3_mad_row(odd, a2 + 1, b2i);
+    b3_mad_row(even, a2, b2i);
+    odd[11] = addc(odd[11], 0);
+    uint32_t m = even[0] * FP_PINV32;
+    b3_mad_row(odd, FP_P.l + 1, m);
+    b3_mad_row(even, FP_P.l, m);
+    odd[11] = addc(odd[11], 0);
+}
+B3_FN void fp_mul2_inl(fp& r, const fp& a1, const fp& b1, const fp& a2, const fp& b2) {
+    uint32_t even[12], odd[12], a1v[12], b1v[12], a2v[12], b2v[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) { a1v[i] = a1.l[i]; b1v[i] = b1.l[i]; a2v[i] = a2.l[i]; b2v[i] = b2.l[i]; }
+#pragma unroll
+    for (int i = 0; i < 12; i += 2) {
+        b3_mont_row2(even, odd, a1v, b1v[i], a2v, b2v[i], i == 0);
+        b3_mont_row2(odd, even, a1v, b1v[i + 1], a2v, b2v[i + 1], false);
+    }
+    even[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+    for (int i = 1; i < 11; i++) even[i] = addc_cc(even[i], odd[i + 1]);
+    even[11] = addc(even[11], 0);
+    fp_final_sub(r, even);
+}
+// Out-of-line multipliers take and return their operands BY VALUE: ptxas then passes them in registers, and the
+// callers' field elements never have their address taken, so they stay in registers instead of the local-memory
+// stack (by-reference noinline calls put every operand through LDL/STL: 113 M local loads in the first Miller
+// kernel, profiles/r1a_miller_full.txt).  The by-reference spellings below are force-inlined shims.
+B3_FN_NOINLINE fp fp_mul_v(fp a, fp b) { fp r; fp_mul_inl(r, a, b); return r; }
+B3_FN_NOINLINE fp fp_mul2_v(fp a1, fp b1, fp a2, fp b2) { fp r; fp_mul2_inl(r, a1, b1, a2, b2); return r; }
+B3_FN void fp_mul2(fp& r, const fp& a1, const fp& b1, const fp& a2, const fp& b2) { r = fp_mul2_v(a1, b1, a2, b2); }
+B3_FN void fp_mul(fp& r, const fp& a, const fp& b) { r = fp_mul_v(a, b); }
+B3_FN void fp_sqr(fp& r, const fp& a) { r = fp_mul_v(a, a); }
 
 // Montgomery form <-> canonical
 B3_FN void fp_to_mont(fp& r, const fp& a) { fp_mul(r, FP_R2, a); }       // a any 384-bit value

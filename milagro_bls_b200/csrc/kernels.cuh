@@ -4,6 +4,7 @@
 #include "h2c.cuh"
 #include "pairing.cuh"
 #include "coop12.cuh"
+#include "fp2h.cuh"
 
 #define B3_ERR_AGGREGATE_EMPTY_POINTS_D (-1)
 #define B3_ERR_INVALID_G1_SIZE_D (-6)
@@ -24,37 +25,31 @@ __global__ void __launch_bounds__(B3_TPB) k_g1_parse(const uint8_t* __restrict__
     out[i] = j;
     status[i] = e;
 }
-// G2 uncompressed wire -> affine struct; optional on-curve check and subgroup check (ok[i])
-__global__ void __launch_bounds__(B3_TPB) k_g2_parse(const uint8_t* __restrict__ in, size_t n, g2_aff* out, int32_t* status, int32_t* ok,
-                                                      int check_curve, int check_subgroup) {
+// G2 uncompressed wire -> affine struct; optional on-curve check
+__global__ void __launch_bounds__(B3_TPB) k_g2_parse(const uint8_t* __restrict__ in, size_t n, g2_aff* out, int32_t* status, int check_curve) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g2_aff a;
     int e = g2_aff_from_wire(a, in + 192 * i);
     if (e == B3_OK && check_curve && !pt_on_curve_aff(a)) e = B3_ERR_INVALID_POINT;
     if (e) { fp2_zero(a.x); fp2_zero(a.y); a.inf = 1; }
-    int good = 1;
-    if (check_subgroup && e == B3_OK) {
-        g2_jac j;
-        pt_from_aff(j, a);
-        good = g2_in_subgroup(j) ? 1 : 0;
-    }
     out[i] = a;
     status[i] = e;
-    if (ok) ok[i] = (e == B3_OK) ? good : 0;
 }
-// subgroup_check_g2 on parsed signatures: ok[i] = parsed fine && in G2 (infinity passes)
+// subgroup_check_g2 on parsed signatures: ok[i] = parsed fine && in G2 (infinity passes).
+// LANE PAIRS (fp2h.cuh): threads (2i, 2i+1) work on signature i.
 __global__ void __launch_bounds__(B3_TPB) k_g2_subgroup(const g2_aff* pts, const int32_t* status, size_t n, int32_t* ok) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     if (i >= n) return;
     int good = 0;
     if (status[i] == B3_OK) {
-        g2_aff a = pts[i];
-        g2_jac j;
+        g2h_aff a;
+        g2h_load(a, pts[i]);
+        g2h_jac j;
         pt_from_aff(j, a);
         good = g2_in_subgroup(j) ? 1 : 0;
     }
-    ok[i] = good;
+    if (!pair_odd()) ok[i] = good;
 }
 // key_validate on parsed G1 points (not infinity, in G1)
 __global__ void __launch_bounds__(B3_TPB) k_g1_key_validate(const g1_jac* pts, const int32_t* status, size_t n, int32_t* valid) {
@@ -303,13 +298,15 @@ __global__ void __launch_bounds__(B3_TPB) k_g1_mul_u64(const g1_jac* in, const u
     pt_mul_u64(r, p, k[i]);
     out[i] = r;
 }
+// [c_j] sig_j, LANE PAIRS: threads (2i, 2i+1) work on signature i
 __global__ void __launch_bounds__(B3_TPB) k_g2_mul_u64(const g2_aff* in, const uint64_t* __restrict__ k, size_t n, g2_jac* out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     if (i >= n) return;
-    g2_aff p = in[i];
-    g2_jac r;
+    g2h_aff p;
+    g2h_load(p, in[i]);
+    g2h_jac r;
     pt_mul_u64_aff(r, p, k[i]);
-    out[i] = r;
+    g2h_store(out[i], r);
 }
 // 256-bit scalars (32-byte big-endian) -- input synthesis only
 __device__ __forceinline__ void load_scalar256(uint32_t* k, const uint8_t* b) {
@@ -346,17 +343,19 @@ __global__ void __launch_bounds__(B3_TPB) k_g2_mul_u256(const uint8_t* __restric
     g2_aff_to_wire(out192 + 192 * i, a);
 }
 
-// pairwise tree level: out[i] = in[2i] + in[2i+1]
+// pairwise tree level: out[i] = in[2i] + in[2i+1]   (LANE PAIRS: threads (2i, 2i+1) work on output i)
 __global__ void __launch_bounds__(B3_TPB) k_g2_add_pairs(const g2_jac* in, size_t n, g2_jac* out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     size_t m = (n + 1) / 2;
     if (i >= m) return;
-    g2_jac a = in[2 * i];
+    g2h_jac a;
+    g2h_load(a, in[2 * i]);
     if (2 * i + 1 < n) {
-        g2_jac b = in[2 * i + 1];
+        g2h_jac b;
+        g2h_load(b, in[2 * i + 1]);
         pt_add(a, a, b);
     }
-    out[i] = a;
+    g2h_store(out[i], a);
 }
 
 // ------------------------------------------------------------------------------------------------ normalisation
@@ -396,37 +395,64 @@ __global__ void k_set_neg_g1(g1_aff* out) {
 }
 
 // ------------------------------------------------------------------------------------------------ hash to G2
+// Two threads per message.  Phase 1: each lane maps ONE of the two field elements to the curve (SSWU + 3-isogeny,
+// single-thread Fp2 arithmetic: the square roots are chains of Fp operations).  Phase 2: the two points are
+// redistributed into lane-pair form and the pair adds them and clears the cofactor together.
 __global__ void __launch_bounds__(B3_TPB) k_hash_to_g2(const uint8_t* __restrict__ msgs, const uint32_t* __restrict__ off, size_t n,
                                                        const uint8_t* __restrict__ dst, uint32_t dst_len, g2_jac* out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     if (i >= n) return;
+    const bool odd = pair_odd();
     uint32_t b = off[i], e = off[i + 1];
-    g2_jac r;
-    hash_to_g2_jac(r, msgs + b, e - b, dst, dst_len);
-    out[i] = r;
+    g2_jac q;
+    {
+        fp2 u0, u1, u;
+        hash_to_field_fp2_x2(u0, u1, msgs + b, e - b, dst, dst_len);
+        fp2_select(u, odd, u1, u0);
+        map_to_curve_g2(q, u);
+    }
+    // even lane holds Q0, odd lane holds Q1 -> (q0, q1) in lane-pair form
+    g2h_jac q0, q1;
+    const fp2* src[3] = {&q.x, &q.y, &q.z};
+    fp2h* d0[3] = {&q0.x, &q0.y, &q0.z};
+    fp2h* d1[3] = {&q1.x, &q1.y, &q1.z};
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        fp send, recv;
+        fp_select(send, odd, src[c]->c0, src[c]->c1);      // even sends its c1 (for the odd lane), odd sends its c0
+        pair_xchg(recv, send);
+        fp_select(d0[c]->v, odd, recv, src[c]->c0);        // Q0: even keeps c0, odd receives Q0.c1
+        fp_select(d1[c]->v, odd, src[c]->c1, recv);        // Q1: even receives Q1.c0, odd keeps c1
+    }
+    pt_add(q0, q0, q1);
+    g2_clear_cofactor(q1, q0);
+    g2h_store(out[i], q1);
 }
 
 // ------------------------------------------------------------------------------------------------ pairing
 // ---- split multi-Miller loop (pairing.cuh: "split Miller loop") ---------------------------------------------------
 // 1. point chain of every pair -> unscaled lines, lines[(slot * n + pair) * 3 + {0,1,2}] = (u0, l3, u5)
+//    LANE PAIRS: threads (2i, 2i+1) run the chain of pair i, each storing its half of every coefficient.
 __global__ void __launch_bounds__(B3_TPB) k_miller_lines(const g2_aff* __restrict__ q, size_t n, fp2* __restrict__ lines) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     if (i >= n) return;
-    g2_aff Q = q[i];
-    if (Q.inf) return;                         // never read: the accumulate kernel skips pairs with an infinite member
-    miller_pt t;
-    t.x = Q.x; t.y = Q.y; fp2_one(t.z);
+    if (q[i].inf) return;                      // never read: the accumulate kernel skips pairs with an infinite member
+    fp2h qx, qy;
+    fp2h_load(qx, q[i].x);
+    fp2h_load(qy, q[i].y);
+    miller_pt_t<fp2h> t;
+    t.x = qx; t.y = qy; fp2_one(t.z);
     const uint64_t x = B3_X_ABS;
     int a = B3_MILLER_DBL_SLOTS;
-    fp2 u0, l3, u5;
+    fp2h u0, l3, u5;
     for (int it = 0; it < B3_MILLER_DBL_SLOTS; it++) {
         miller_dbl_step_u(t, u0, l3, u5);
         fp2* o = lines + ((size_t)it * n + i) * 3;
-        o[0] = u0; o[1] = l3; o[2] = u5;
+        fp2h_store(o[0], u0); fp2h_store(o[1], l3); fp2h_store(o[2], u5);
         if ((x >> (62 - it)) & 1) {
-            miller_add_step_u(t, u0, l3, u5, Q.x, Q.y);
+            miller_add_step_u(t, u0, l3, u5, qx, qy);
             o = lines + ((size_t)a * n + i) * 3;
-            o[0] = u0; o[1] = l3; o[2] = u5;
+            fp2h_store(o[0], u0); fp2h_store(o[1], l3); fp2h_store(o[2], u5);
             a++;
         }
     }

@@ -95,8 +95,13 @@ B3_FN_NOINLINE void miller_add_step(miller_pt& t, fp2& l0, fp2& l3, fp2& l5, con
 #define B3_MILLER_DBL_SLOTS 63
 #define B3_MILLER_SLOTS 68
 // Unscaled doubling step.  Full line: l0 = u0 * (-yP),  l3,  l5 = u5 * xP   with u0 = xi (2YZ), u5 = 3 X^2.
-B3_FN_NOINLINE void miller_dbl_step_u(miller_pt& t, fp2& u0, fp2& l3, fp2& u5) {
-    fp2 a, b, c, e, f, g, h, j, e2, u;
+template <class F2>
+struct miller_pt_t {
+    F2 x, y, z;
+};
+template <class F2>
+B3_FN_NOINLINE void miller_dbl_step_u(miller_pt_t<F2>& t, F2& u0, F2& l3, F2& u5) {
+    F2 a, b, c, e, f, g, h, j, e2, u;
     fp2_mul(a, t.x, t.y);
     fp2_half(a, a);                 // A = XY/2
     fp2_sqr(b, t.y);                // B = Y^2
@@ -124,8 +129,9 @@ B3_FN_NOINLINE void miller_dbl_step_u(miller_pt& t, fp2& u0, fp2& l3, fp2& u5) {
 }
 // Unscaled addition step, signs arranged so that the same factors (-yP, xP) apply as for a doubling line:
 //   l0 = u0 * (-yP), l3, l5 = u5 * xP   with u0 = -xi lambda, u5 = -theta.
-B3_FN_NOINLINE void miller_add_step_u(miller_pt& t, fp2& u0, fp2& l3, fp2& u5, const fp2& xq, const fp2& yq) {
-    fp2 theta, lambda, c, d, e, f, g, h, u;
+template <class F2>
+B3_FN_NOINLINE void miller_add_step_u(miller_pt_t<F2>& t, F2& u0, F2& l3, F2& u5, const F2& xq, const F2& yq) {
+    F2 theta, lambda, c, d, e, f, g, h, u;
     fp2_mul(u, yq, t.z);
     fp2_sub(theta, t.y, u);
     fp2_mul(u, xq, t.z);

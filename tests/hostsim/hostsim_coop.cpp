@@ -13,6 +13,14 @@ static void fp12_in(fp12& r, const uint8_t* b) {      // wire order w^0,w^3,w^1,
 }
 
 extern "C" {
+// out = a1*b1 + a2*b2 mod p through the dual-product Montgomery routine (fp.cuh: fp_mul2)
+void hc_fp_mul2(const uint8_t* a1, const uint8_t* b1, const uint8_t* a2, const uint8_t* b2, uint8_t* out) {
+    fp x1, y1, x2, y2, r, t;
+    fp_in(x1, a1); fp_in(y1, b1); fp_in(x2, a2); fp_in(y2, b2);
+    fp_mul2(r, x1, y1, x2, y2);
+    fp_from_mont(t, r);
+    fp_raw_to_be(out, t);
+}
 // op: 0 mul, 1 conj, 2 frob, 3 frob2, 4 frob3, 5 pow_x, 6 pow_x_half, 7 final_exp
 void hc_fp12_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     static coop_fexp_ws s;
@@ -43,7 +51,7 @@ int hc_multi_pairing_split(const uint8_t* q192s, const uint8_t* p96s, int n, uin
         if ((e = g2_aff_from_wire(Q, q192s + 192 * i))) return e;
         if ((e = g1_aff_from_wire(P, p96s + 96 * i))) return e;
         if (Q.inf || P.inf) continue;
-        miller_pt t; t.x = Q.x; t.y = Q.y; fp2_one(t.z);
+        miller_pt_t<fp2> t; t.x = Q.x; t.y = Q.y; fp2_one(t.z);
         fp nyp; fp_neg(nyp, P.y);
         int a = B3_MILLER_DBL_SLOTS;
         for (int it = 0; it < B3_MILLER_DBL_SLOTS; it++) {

@@ -301,3 +301,13 @@ def test_split_miller_loop(hc):
     assert hc.hc_multi_pairing_split(g2w(sig) + g2w(H2), ps, 2, gt) == 0
     assert gt.raw == O.f12_to_bytes(O.fexp(O.ate2(sig, O.NEG_G1, H2, pk)))
     assert hc.hc_multi_pairing_split(g2w(None) + g2w(H), g1w(pk) + g1w(None), 2, gt) == 0 and gt.raw == O.f12_to_bytes(O.F12_ONE)
+
+
+def test_fp_mul2(hc):
+    edge = [0, 1, p - 1, p - 2, (1 << 380), p >> 1]
+    cases = [(rfp(), rfp(), rfp(), rfp()) for _ in range(200)]
+    cases += [(a, b, c, d) for a in edge for b in edge[:3] for c in edge[1:4] for d in edge[2:5]]
+    for a1, b1, a2, b2 in cases:
+        out = ctypes.create_string_buffer(48)
+        hc.hc_fp_mul2(b48(a1), b48(b1), b48(a2), b48(b2), out)
+        assert int.from_bytes(out.raw, "big") == (a1 * b1 + a2 * b2) % p
