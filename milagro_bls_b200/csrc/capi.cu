@@ -47,7 +47,7 @@ struct b3_ctx {
     int serial = 0;
     // scratch (grown on demand, reused across calls)
     dev_buf in_a, in_b, in_c, in_d, in_e, in_f;      // staged host inputs
-    dev_buf g1j, g1j2, g1a, g2a_sig, g2j, g2j2, g2j_h, g2a, f12a, f12b, lines, status, ok, misc, outb;
+    dev_buf g1j, g1j2, g1a, g2a_sig, g2j, g2j2, g2j_h, g2a, g2q, g1pp, qinf, f12a, f12b, lines, status, ok, misc, outb;
     uint8_t* d_dst = nullptr;
 };
 
@@ -119,7 +119,7 @@ extern "C" void b3_ctx_destroy(b3_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     dev_buf* bufs[] = {&ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->in_d, &ctx->in_e, &ctx->in_f, &ctx->g1j, &ctx->g1j2, &ctx->g1a,
-                       &ctx->g2a_sig, &ctx->g2j, &ctx->g2j2, &ctx->g2j_h, &ctx->g2a, &ctx->lines, &ctx->f12a, &ctx->f12b, &ctx->status, &ctx->ok,
+                       &ctx->g2a_sig, &ctx->g2j, &ctx->g2j2, &ctx->g2j_h, &ctx->g2a, &ctx->g2q, &ctx->g1pp, &ctx->qinf, &ctx->lines, &ctx->f12a, &ctx->f12b, &ctx->status, &ctx->ok,
                        &ctx->misc, &ctx->outb};
     for (dev_buf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_dst) cudaFree(ctx->d_dst);
@@ -207,7 +207,7 @@ static int g2_sum(b3_ctx* ctx, g2_jac* a, g2_jac* b, size_t n, g2_jac** res) {
 }
 // Miller loops over n_pairs (q[i], p[i]) -> product left in *res.  Split multi-Miller loop (pairing.cuh):
 // point chains -> lines in HBM (68 x n x 288 B), per-slot accumulation over all pairs, one cooperative closing chain.
-static int miller_product(b3_ctx* ctx, const g2_aff* q, const g1_aff* p, size_t n_pairs, fp12** res) {
+static int miller_product(b3_ctx* ctx, const g2_jac* q, const g1_pp* p, size_t n_pairs, fp12** res) {
     size_t chunks = (n_pairs + 1024) / 2048;              // ~16 pairs per accumulating thread
     if (chunks < 1) chunks = 1;
     if (chunks > 64) chunks = 64;
@@ -222,13 +222,15 @@ static int miller_product(b3_ctx* ctx, const g2_aff* q, const g1_aff* p, size_t 
         return B3_OK;
     }
     CKR(ensure(ctx, ctx->lines, sizeof(fp2) * 3 * B3_MILLER_SLOTS * n_pairs));
+    CKR(ensure(ctx, ctx->qinf, 4 * n_pairs));
     fp2* lines = (fp2*)ctx->lines.p;
+    uint32_t* qinf = (uint32_t*)ctx->qinf.p;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     int sp = span_begin(ctx, ST_MILLER_LINES, ctx->stream);
-    LAUNCH(k_miller_lines, nblk(2 * n_pairs), B3_TPB, q, n_pairs, lines);
+    LAUNCH(k_miller_lines, nblk(2 * n_pairs), B3_TPB, q, n_pairs, lines, qinf);
     span_end(ctx, sp, ctx->stream);
     sp = span_begin(ctx, ST_MILLER, ctx->stream);
-    LAUNCH(k_miller_accum, dim3((unsigned)chunks, B3_MILLER_SLOTS), B3_TPB, (const fp2*)lines, q, p, n_pairs, K, partial);
+    LAUNCH(k_miller_accum, dim3((unsigned)chunks, B3_MILLER_SLOTS), B3_TPB, (const fp2*)lines, (const uint32_t*)qinf, p, n_pairs, K, partial);
     span_end(ctx, sp, ctx->stream);
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     sp = span_begin(ctx, ST_FP12_PRODUCT, ctx->stream);
@@ -422,6 +424,11 @@ static int stage_dst(b3_ctx* ctx, const uint8_t* dst, size_t dst_len, const uint
     *len = (uint32_t)dst_len;
     return B3_OK;
 }
+// hash_to_curve_g2 left in Jacobian coordinates (pair members of the Miller loop are never normalised)
+static int hash_to_g2_jac_dev(b3_ctx* ctx, cudaStream_t strm, const uint8_t* d_msgs, const uint32_t* d_off, size_t n, g2_jac* d_out) {
+    LAUNCH_ON(strm, k_hash_to_g2, nblk(2 * n), B3_TPB, d_msgs, d_off, n, (const uint8_t*)ctx->d_dst, (uint32_t)kDstG2Len, d_out);
+    return B3_OK;
+}
 static int hash_to_g2_affine_dev(b3_ctx* ctx, cudaStream_t strm, const uint8_t* d_msgs, const uint32_t* d_off, size_t n, const uint8_t* d_dst,
                                  uint32_t dst_len, g2_aff* d_out) {
     CKR(ensure(ctx, ctx->g2j_h, sizeof(g2_jac) * n));
@@ -472,24 +479,24 @@ static int verify_two_pairs(b3_ctx* ctx, const g2_aff* d_sig, const int32_t* d_s
     uint32_t off[2] = {0, (uint32_t)msg_len};
     CKR(h2d(ctx, ctx->in_c, msg, msg_len));
     CKR(h2d(ctx, ctx->in_d, off, 8));
-    CKR(ensure(ctx, ctx->g2a, sizeof(g2_aff) * 2));
-    CKR(ensure(ctx, ctx->g1a, sizeof(g1_aff) * 2));
-    g2_aff* q = (g2_aff*)ctx->g2a.p;
-    g1_aff* p = (g1_aff*)ctx->g1a.p;
+    CKR(ensure(ctx, ctx->g2q, sizeof(g2_jac) * 2));
+    CKR(ensure(ctx, ctx->g1pp, sizeof(g1_pp) * 2));
+    g2_jac* q = (g2_jac*)ctx->g2q.p;
+    g1_pp* p = (g1_pp*)ctx->g1pp.p;
     // pair 0: (sig, -G1)
-    CK(cudaMemcpyAsync(q, d_sig, sizeof(g2_aff), cudaMemcpyDeviceToDevice, ctx->stream));
-    LAUNCH(k_set_neg_g1, 1, 1, p);
+    LAUNCH(k_g2_aff_to_jac, 1, B3_TPB, d_sig, 1, q);
+    LAUNCH(k_set_neg_g1_pp, 1, 1, p);
     // pair 1: (H(msg), key)
-    CKR(hash_to_g2_affine_dev(ctx, ctx->stream, (const uint8_t*)ctx->in_c.p, (const uint32_t*)ctx->in_d.p, 1, ctx->d_dst, (uint32_t)kDstG2Len, q + 1));
-    LAUNCH(k_g1_to_affine, 1, B3_TPB, d_key, 1, p + 1);
+    CKR(hash_to_g2_jac_dev(ctx, ctx->stream, (const uint8_t*)ctx->in_c.p, (const uint32_t*)ctx->in_d.p, 1, q + 1));
+    LAUNCH(k_g1_jac_to_pp, 1, B3_TPB, d_key, 1, p + 1);
     fp12* res;
     CKR(miller_product(ctx, q, p, 2, &res));
     int ok = 0;
     CKR(finish(ctx, res, &ok, gt576));
     int32_t sig_ok = 0;
-    g1_aff key;
+    g1_pp key;
     CKR(d2h(ctx, &sig_ok, d_sig_ok, 4));
-    CKR(d2h(ctx, &key, p + 1, sizeof(g1_aff)));
+    CKR(d2h(ctx, &key, p + 1, sizeof(g1_pp)));
     CKR(sync(ctx));
     if (!sig_ok) ok = 0;
     if (reject_inf_key && key.inf) ok = 0;
@@ -560,18 +567,18 @@ extern "C" int b3_aggregate_verify(b3_ctx* ctx, const uint8_t sig192[192], const
     CKR(h2d(ctx, ctx->in_c, msgs, msg_off[n]));
     CKR(h2d(ctx, ctx->in_d, msg_off, 4 * (n + 1)));
     CKR(ensure(ctx, ctx->g1j, sizeof(g1_jac) * n));
-    CKR(ensure(ctx, ctx->g1a, sizeof(g1_aff) * (n + 1)));
-    CKR(ensure(ctx, ctx->g2a, sizeof(g2_aff) * (n + 1)));
+    CKR(ensure(ctx, ctx->g1pp, sizeof(g1_pp) * (n + 1)));
+    CKR(ensure(ctx, ctx->g2q, sizeof(g2_jac) * (n + 1)));
     CKR(ensure(ctx, ctx->status, 4 * (n + 4)));
     int32_t* d_st = (int32_t*)ctx->status.p + 4;
     LAUNCH(k_g1_parse, nblk(n), B3_TPB, (const uint8_t*)ctx->in_b.p, n, (g1_jac*)ctx->g1j.p, d_st, 1);
     CKR(first_status(ctx, d_st, n));
-    g2_aff* q = (g2_aff*)ctx->g2a.p;
-    g1_aff* p = (g1_aff*)ctx->g1a.p;
-    LAUNCH(k_g1_to_affine, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j.p, n, p);       // Z = 1: no inversion needed... (generic path)
-    CKR(hash_to_g2_affine_dev(ctx, ctx->stream, (const uint8_t*)ctx->in_c.p, (const uint32_t*)ctx->in_d.p, n, ctx->d_dst, (uint32_t)kDstG2Len, q));
-    CK(cudaMemcpyAsync(q + n, ctx->g2a_sig.p, sizeof(g2_aff), cudaMemcpyDeviceToDevice, ctx->stream));
-    LAUNCH(k_set_neg_g1, 1, 1, p + n);
+    g2_jac* q = (g2_jac*)ctx->g2q.p;
+    g1_pp* p = (g1_pp*)ctx->g1pp.p;
+    LAUNCH(k_g1_jac_to_pp, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j.p, n, p);
+    CKR(hash_to_g2_jac_dev(ctx, ctx->stream, (const uint8_t*)ctx->in_c.p, (const uint32_t*)ctx->in_d.p, n, q));
+    LAUNCH(k_g2_aff_to_jac, 1, B3_TPB, (const g2_aff*)ctx->g2a_sig.p, 1, q + n);
+    LAUNCH(k_set_neg_g1_pp, 1, 1, p + n);
     fp12* res;
     CKR(miller_product(ctx, q, p, n + 1, &res));
     int ok = 0;
@@ -592,8 +599,8 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
     CKR(ensure(ctx, ctx->ok, 4 * (n + 8)));
     CKR(ensure(ctx, ctx->g1j, sizeof(g1_jac) * (n + 1)));
     CKR(ensure(ctx, ctx->g1j2, sizeof(g1_jac) * (n + 1)));
-    CKR(ensure(ctx, ctx->g1a, sizeof(g1_aff) * (n + 1)));
-    CKR(ensure(ctx, ctx->g2a, sizeof(g2_aff) * (n + 1)));
+    CKR(ensure(ctx, ctx->g1pp, sizeof(g1_pp) * (n + 1)));
+    CKR(ensure(ctx, ctx->g2q, sizeof(g2_jac) * (n + 1)));
     CKR(ensure(ctx, ctx->g2j2, sizeof(g2_jac) * (n + 2)));
     CKR(ensure(ctx, ctx->misc, 64));
     int32_t* d_st_sig = (int32_t*)ctx->status.p;
@@ -601,11 +608,10 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
     long long* d_first_bad = (long long*)ctx->misc.p;
     long long init = 0x7fffffffffffffffLL;
     CK(cudaMemcpyAsync(d_first_bad, &init, 8, cudaMemcpyHostToDevice, ctx->stream));
-    g2_aff* q = (g2_aff*)ctx->g2a.p;
-    g1_aff* p = (g1_aff*)ctx->g1a.p;
+    g2_jac* q = (g2_jac*)ctx->g2q.p;
+    g1_pp* p = (g1_pp*)ctx->g1pp.p;
     if (n > 0) {
         CKR(ensure(ctx, ctx->g2j, sizeof(g2_jac) * (n + 1)));
-        CKR(ensure(ctx, ctx->g2j_h, sizeof(g2_jac) * (n + 1)));
         // The four stages below are independent of each other; unless ctx->serial they run concurrently:
         //   main : parse signatures -> S = sum_j [c_j] sig_j            aux0 : subgroup checks of the parsed signatures
         //   aux1 : aggregate keys -> P_j = [c_j] apk_j                  aux2 : H_j = hash_to_curve_g2(msg_j)
@@ -641,20 +647,19 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
         }
         span_end(ctx, sp, s1);
         sp = span_begin(ctx, ST_G1_MUL, s1);
-        LAUNCH_ON(s1, k_g1_mul_u64, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j.p, d_scalars, n, (g1_jac*)ctx->g1j2.p);
-        LAUNCH_ON(s1, k_g1_to_affine, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j2.p, n, p);
-        LAUNCH_ON(s1, k_set_neg_g1, 1, 1, p + n);
+        LAUNCH_ON(s1, k_g1_mul_u64_pp, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j.p, d_scalars, n, p);
+        LAUNCH_ON(s1, k_set_neg_g1_pp, 1, 1, p + n);
         span_end(ctx, sp, s1);
         // 4. H_j = hash_to_curve_g2(msg_j), affine (M/src/aggregates.rs:290,296)
         sp = span_begin(ctx, ST_HASH_TO_G2, s2);
-        CKR(hash_to_g2_affine_dev(ctx, s2, d_msgs, d_msg_off, n, ctx->d_dst, (uint32_t)kDstG2Len, q));
+        CKR(hash_to_g2_jac_dev(ctx, s2, d_msgs, d_msg_off, n, q));
         span_end(ctx, sp, s2);
         // 5. S = sum_j [c_j] sig_j (M/src/aggregates.rs:303)
         sp = span_begin(ctx, ST_G2_MUL_SUM, sm);
         LAUNCH_ON(sm, k_g2_mul_u64, nblk(2 * n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, d_scalars, n, (g2_jac*)ctx->g2j.p);
         g2_jac* s;
         CKR(g2_sum(ctx, (g2_jac*)ctx->g2j.p, (g2_jac*)ctx->g2j2.p, n, &s));
-        LAUNCH_ON(sm, k_g2_to_affine, 1, B3_TPB, (const g2_jac*)s, 1, q + n);
+        CK(cudaMemcpyAsync(q + n, s, sizeof(g2_jac), cudaMemcpyDeviceToDevice, sm));
         span_end(ctx, sp, sm);
         if (!ctx->serial) {
             cudaStream_t auxs[3] = {s0, s1, s2};

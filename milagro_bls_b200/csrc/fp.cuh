@@ -306,7 +306,56 @@ B3_FN_NOINLINE void fp_pow_const(fp& r, const fp& a, const fp& e) {
     r = acc;
 }
 
-B3_FN void fp_inv(fp& r, const fp& a) { fp_pow_const(r, a, FP_EXP_INV); }   // 0 -> 0
+// canonical integer comparison (inputs are plain 384-bit integers)
+B3_FN bool fp_raw_gt(const fp& a, const fp& b) {      // a > b
+    uint32_t t = sub_cc(b.l[0], a.l[0]);
+#pragma unroll
+    for (int i = 1; i < 12; i++) t = subc_cc(b.l[i], a.l[i]);
+    (void)t;
+    return subc(0, 0) != 0;
+}
+B3_FN bool fp_raw_is_one(const fp& a) {
+    uint32_t t = a.l[0] ^ 1u;
+#pragma unroll
+    for (int i = 1; i < 12; i++) t |= a.l[i];
+    return t == 0;
+}
+// 1/a mod p (0 -> 0) by the binary extended Euclidean algorithm on the Montgomery representative, about 5x fewer
+// instructions than the Fermat exponentiation a^(p-2) the reference uses (A/fp.rs:608-616); the value is the same.
+// With abar = a R: the loop yields abar^-1 = a^-1 R^-1 as a plain integer; one multiplication by R^3 gives a^-1 R.
+// Data-dependent control flow (the operand is public on this path).
+B3_FN_NOINLINE void fp_inv(fp& r, const fp& a) {
+    if (fp_is_zero(a)) { r = FP_NIL; return; }
+    fp u = a, v = FP_P, x1 = FP_RAW_ONE, x2 = FP_NIL;
+    while (!fp_raw_is_one(u) && !fp_raw_is_one(v)) {
+        if (!(u.l[0] & 1u)) {
+#pragma unroll
+            for (int i = 0; i < 11; i++) u.l[i] = (u.l[i] >> 1) | (u.l[i + 1] << 31);
+            u.l[11] >>= 1;
+            fp_half(x1, x1);
+        } else if (!(v.l[0] & 1u)) {
+#pragma unroll
+            for (int i = 0; i < 11; i++) v.l[i] = (v.l[i] >> 1) | (v.l[i + 1] << 31);
+            v.l[11] >>= 1;
+            fp_half(x2, x2);
+        } else if (fp_raw_gt(u, v)) {
+            u.l[0] = sub_cc(u.l[0], v.l[0]);
+#pragma unroll
+            for (int i = 1; i < 11; i++) u.l[i] = subc_cc(u.l[i], v.l[i]);
+            u.l[11] = subc(u.l[11], v.l[11]);
+            fp_sub(x1, x1, x2);
+        } else {
+            v.l[0] = sub_cc(v.l[0], u.l[0]);
+#pragma unroll
+            for (int i = 1; i < 11; i++) v.l[i] = subc_cc(v.l[i], u.l[i]);
+            v.l[11] = subc(v.l[11], u.l[11]);
+            fp_sub(x2, x2, x1);
+        }
+    }
+    fp t;
+    fp_select(t, fp_raw_is_one(u), x1, x2);
+    fp_mul(r, t, FP_R3);
+}
 
 // Square root helper for p = 3 mod 4.  Given d, g = d^((p-3)/4):
 //   t = g*d, chi = t*g = d^((p-1)/2) in {0, 1, -1}.  If chi == 1: t^2 = d and 1/t = g.
@@ -326,13 +375,6 @@ B3_FN_NOINLINE bool fp_sqrt_ratio_parts(fp& t, fp& tinv, const fp& d) {
 }
 
 // canonical integer comparison helpers (inputs canonical, NOT Montgomery)
-B3_FN bool fp_raw_gt(const fp& a, const fp& b) {      // a > b
-    uint32_t t = sub_cc(b.l[0], a.l[0]);
-#pragma unroll
-    for (int i = 1; i < 12; i++) t = subc_cc(b.l[i], a.l[i]);
-    (void)t;
-    return subc(0, 0) != 0;
-}
 B3_FN bool fp_raw_lt_p(const fp& a) { return fp_raw_gt(FP_P, a); }
 
 // 48 big-endian bytes <-> raw limbs

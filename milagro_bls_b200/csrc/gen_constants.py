@@ -173,6 +173,7 @@ out.append(fp_c("FP_P", p, raw=True))
 out.append(fp_c("FP_NIL", 0, raw=True))
 out.append(fp_c("FP_ONE", 1))
 out.append(fp_c("FP_RAW_ONE", 1, raw=True))
+out.append(fp_c("FP_M_ONE", p - 1))
 out.append(fp_c("FP_R2", R % p))                 # mont(R)   = R^2 mod p
 out.append(fp_c("FP_R3", R * R % p))             # mont(R^2) = R^3 mod p
 out.append("#define FP_PINV32 0x%08xu   /* -p^-1 mod 2^32 */" % ((-pow(p, -1, 1 << 32)) % (1 << 32)))

@@ -158,21 +158,10 @@ B3_FN_NOINLINE void sswu_g2(fp2& xn, fp2& xd, fp2& y, const fp2& u, fp2* dbg = n
     fp2_mul(t, t, xn);
     fp2_mul(t2, gxd, SSWU_B);
     fp2_add(gxn, t, t2);
-    // sqrt(gxn/gxd) = sqrt(gxn * conj(gxd) * N(gxd)) / N(gxd)
-    fp n, s;
-    fp_sqr(n, gxd.c0);
-    fp_sqr(s, gxd.c1);
-    fp_add(n, n, s);
-    fp2 wv, root;
-    fp2_conj(t, gxd);
-    fp2_mul(wv, gxn, t);
-    fp2_mul_fp(wv, wv, n);
-    bool sq = fp2_sqrt_or_z(root, wv);          // sqrt(W) or sqrt(Z W)
-    fp ninv;
-    fp_inv(ninv, n);
-    if (dbg) dbg[0] = root;
-    fp2_mul_fp(root, root, ninv);               // sqrt(gx1) or sqrt(Z gx1)
-    if (dbg) dbg[1] = root;
+    // y1 = sqrt(gxn / gxd) or, if that is not a square, sqrt(Z gxn / gxd): two Fp exponentiations, no inversion
+    fp2 root;
+    bool sq = fp2_sqrt_ratio_or_z(root, gxn, gxd);
+    if (dbg) { dbg[0] = root; dbg[1] = root; }
     if (!sq) {
         fp2_mul(xn, xn, tv1);                   // x2 = tv1 x1
         fp2_mul(t, tv1, u);

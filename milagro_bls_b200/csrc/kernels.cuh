@@ -290,14 +290,6 @@ __global__ void __launch_bounds__(B3_TPB) k_g2_aggregate(const uint8_t* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ scalar multiplication
-// P_j = [c_j] apk_j (Jacobian in, Jacobian out)
-__global__ void __launch_bounds__(B3_TPB) k_g1_mul_u64(const g1_jac* in, const uint64_t* __restrict__ k, size_t n, g1_jac* out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    g1_jac p = in[i], r;
-    pt_mul_u64(r, p, k[i]);
-    out[i] = r;
-}
 // [c_j] sig_j, LANE PAIRS: threads (2i, 2i+1) work on signature i
 __global__ void __launch_bounds__(B3_TPB) k_g2_mul_u64(const g2_aff* in, const uint64_t* __restrict__ k, size_t n, g2_jac* out) {
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
@@ -387,13 +379,6 @@ __global__ void __launch_bounds__(B3_TPB) k_g2_aff_to_wire(const g2_aff* in, siz
     g2_aff a = in[i];
     g2_aff_to_wire(out + 192 * i, a);
 }
-// constant pair member: -G1 generator
-__global__ void k_set_neg_g1(g1_aff* out) {
-    g1_aff a;
-    a.x = G1_GEN_X; a.y = G1_GEN_NEG_Y; a.inf = 0;
-    *out = a;
-}
-
 // ------------------------------------------------------------------------------------------------ hash to G2
 // Two threads per message.  Phase 1: each lane maps ONE of the two field elements to the curve (SSWU + 3-isogeny,
 // single-thread Fp2 arithmetic: the square roots are chains of Fp operations).  Phase 2: the two points are
@@ -430,18 +415,70 @@ __global__ void __launch_bounds__(B3_TPB) k_hash_to_g2(const uint8_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------ pairing
+// G1 member of a pairing in the form the line scaling wants: for P = (X : Y : Z) Jacobian (x = X/Z^2, y = Y/Z^3)
+// the line  l0 = u0 (-y), l3, l5 = u5 x  times Z^3 is  u0 (-Y), l3 Z^3, u5 (X Z)  -- no inversion.
+struct g1_pp {
+    fp xz, ny, z3;
+    uint32_t inf;
+};
+B3_FN void g1_pp_from_jac(g1_pp& r, const g1_jac& p) {
+    fp z2;
+    fp_sqr(z2, p.z);
+    fp_mul(r.xz, p.x, p.z);
+    fp_neg(r.ny, p.y);
+    fp_mul(r.z3, z2, p.z);
+    r.inf = pt_is_inf(p) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(B3_TPB) k_g1_jac_to_pp(const g1_jac* in, size_t n, g1_pp* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_jac p = in[i];
+    g1_pp r;
+    g1_pp_from_jac(r, p);
+    out[i] = r;
+}
+// P_j = [c_j] apk_j straight into pairing form
+__global__ void __launch_bounds__(B3_TPB) k_g1_mul_u64_pp(const g1_jac* in, const uint64_t* __restrict__ k, size_t n, g1_pp* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_jac p = in[i], r;
+    pt_mul_u64(r, p, k[i]);
+    g1_pp o;
+    g1_pp_from_jac(o, r);
+    out[i] = o;
+}
+// constant pair member: -G1 generator
+__global__ void k_set_neg_g1_pp(g1_pp* out) {
+    g1_pp a;
+    a.xz = G1_GEN_X; a.ny = G1_GEN_Y; a.z3 = FP_ONE; a.inf = 0;       // -( -y ) = y
+    *out = a;
+}
+// parsed affine signature -> Jacobian pair member
+__global__ void __launch_bounds__(B3_TPB) k_g2_aff_to_jac(const g2_aff* in, size_t n, g2_jac* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g2_aff a = in[i];
+    g2_jac j;
+    pt_from_aff(j, a);
+    out[i] = j;
+}
+
 // ---- split multi-Miller loop (pairing.cuh: "split Miller loop") ---------------------------------------------------
 // 1. point chain of every pair -> unscaled lines, lines[(slot * n + pair) * 3 + {0,1,2}] = (u0, l3, u5)
 //    LANE PAIRS: threads (2i, 2i+1) run the chain of pair i, each storing its half of every coefficient.
-__global__ void __launch_bounds__(B3_TPB) k_miller_lines(const g2_aff* __restrict__ q, size_t n, fp2* __restrict__ lines) {
+__global__ void __launch_bounds__(B3_TPB) k_miller_lines(const g2_jac* __restrict__ q, size_t n, fp2* __restrict__ lines, uint32_t* __restrict__ qinf) {
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     if (i >= n) return;
-    if (q[i].inf) return;                      // never read: the accumulate kernel skips pairs with an infinite member
-    fp2h qx, qy;
-    fp2h_load(qx, q[i].x);
-    fp2h_load(qy, q[i].y);
-    miller_pt_t<fp2h> t;
-    t.x = qx; t.y = qy; fp2_one(t.z);
+    fp2h X, Y, Z;
+    fp2h_load(X, q[i].x);
+    fp2h_load(Y, q[i].y);
+    fp2h_load(Z, q[i].z);
+    const bool inf = fp2_is_zero(Z);
+    if (!pair_odd()) qinf[i] = inf ? 1u : 0u;
+    if (inf) return;                           // its lines are never read: the accumulate kernel skips the pair
+    miller_pt_t<fp2h> t, Q;
+    miller_start(t, X, Y, Z);
+    Q = t;
     const uint64_t x = B3_X_ABS;
     int a = B3_MILLER_DBL_SLOTS;
     fp2h u0, l3, u5;
@@ -450,7 +487,7 @@ __global__ void __launch_bounds__(B3_TPB) k_miller_lines(const g2_aff* __restric
         fp2* o = lines + ((size_t)it * n + i) * 3;
         fp2h_store(o[0], u0); fp2h_store(o[1], l3); fp2h_store(o[2], u5);
         if ((x >> (62 - it)) & 1) {
-            miller_add_step_u(t, u0, l3, u5, qx, qy);
+            miller_add_step_u(t, u0, l3, u5, Q.x, Q.y, Q.z);
             o = lines + ((size_t)a * n + i) * 3;
             fp2h_store(o[0], u0); fp2h_store(o[1], l3); fp2h_store(o[2], u5);
             a++;
@@ -460,8 +497,8 @@ __global__ void __launch_bounds__(B3_TPB) k_miller_lines(const g2_aff* __restric
 // 2. slot accumulators.  grid = (chunks, B3_MILLER_SLOTS), block = 128: thread g of slot s folds the lines of pairs
 //    [g K, (g+1) K) into a dense Fp12 (sparse multiplications), the warp reduces by a shuffle tree of Fp12 products,
 //    the four warp results are multiplied CTA-cooperatively; partial[s * chunks + chunk] = product of the CTA's lines.
-__global__ void __launch_bounds__(B3_TPB) k_miller_accum(const fp2* __restrict__ lines, const g2_aff* __restrict__ q,
-                                                         const g1_aff* __restrict__ p, size_t n, unsigned K, fp12* partial) {
+__global__ void __launch_bounds__(B3_TPB) k_miller_accum(const fp2* __restrict__ lines, const uint32_t* __restrict__ qinf,
+                                                         const g1_pp* __restrict__ p, size_t n, unsigned K, fp12* partial) {
     __shared__ fp12 wres[B3_TPB / 32];
     __shared__ coop_ws ws;
     const unsigned slot = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
@@ -471,13 +508,12 @@ __global__ void __launch_bounds__(B3_TPB) k_miller_accum(const fp2* __restrict__
     fp12 acc;
     bool have = false;
     for (size_t j = b; j < e; j++) {
-        if (q[j].inf || p[j].inf) continue;
+        if (qinf[j] || p[j].inf) continue;
         const fp2* l = lines + ((size_t)slot * n + j) * 3;
-        fp xp = p[j].x, nyp;
-        fp_neg(nyp, p[j].y);
-        fp2 l0, l3 = l[1], l5;
-        fp2_mul_fp(l0, l[0], nyp);
-        fp2_mul_fp(l5, l[2], xp);
+        fp2 l0, l3, l5;                                    // the line times Z_P^3 (an Fp factor)
+        fp2_mul_fp(l0, l[0], p[j].ny);
+        fp2_mul_fp(l3, l[1], p[j].z3);
+        fp2_mul_fp(l5, l[2], p[j].xz);
         if (have) fp12_mul_by_line(acc, l0, l3, l5);
         else { fp12_from_line(acc, l0, l3, l5); have = true; }
     }

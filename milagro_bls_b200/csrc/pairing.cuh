@@ -127,35 +127,53 @@ B3_FN_NOINLINE void miller_dbl_step_u(miller_pt_t<F2>& t, F2& u0, F2& l3, F2& u5
     fp2_sub(t.y, g, u);             // Y3 = G^2 - 3 E^2
     fp2_mul(t.z, b, h);             // Z3 = B H
 }
-// Unscaled addition step, signs arranged so that the same factors (-yP, xP) apply as for a doubling line:
-//   l0 = u0 * (-yP), l3, l5 = u5 * xP   with u0 = -xi lambda, u5 = -theta.
+// Unscaled addition step T <- T + Q with Q = (X2 : Y2 : Z2) homogeneous projective (x2 = X2/Z2, y2 = Y2/Z2), so that
+// hash_to_curve outputs never have to be normalised.  It is the mixed step (A/pair.rs:88-133) with theta, lambda and
+// the new point scaled by powers of Z2 -- Fp2 factors, which vanish in the final exponentiation.  Signs are arranged
+// so that the same factors (-yP, xP) apply as for a doubling line:
+//   l0 = u0 * (-yP), l3, l5 = u5 * xP   with u0 = -xi lambda Z2, l3 = theta X2 - lambda Y2, u5 = -theta Z2,
+//   theta = Y1 Z2 - Y2 Z1,  lambda = X1 Z2 - X2 Z1.
 template <class F2>
-B3_FN_NOINLINE void miller_add_step_u(miller_pt_t<F2>& t, F2& u0, F2& l3, F2& u5, const F2& xq, const F2& yq) {
-    F2 theta, lambda, c, d, e, f, g, h, u;
+B3_FN_NOINLINE void miller_add_step_u(miller_pt_t<F2>& t, F2& u0, F2& l3, F2& u5, const F2& xq, const F2& yq, const F2& zq) {
+    F2 theta, lambda, c, d, e, f, g, h, u, xz, yz, zz;
+    fp2_mul(xz, t.x, zq);
+    fp2_mul(yz, t.y, zq);
+    fp2_mul(zz, t.z, zq);
     fp2_mul(u, yq, t.z);
-    fp2_sub(theta, t.y, u);
+    fp2_sub(theta, yz, u);
     fp2_mul(u, xq, t.z);
-    fp2_sub(lambda, t.x, u);
+    fp2_sub(lambda, xz, u);
     fp2_sqr(c, theta);
     fp2_sqr(d, lambda);
     fp2_mul(e, lambda, d);
-    fp2_mul(f, t.z, c);
-    fp2_mul(g, t.x, d);
+    fp2_mul(f, zz, c);
+    fp2_mul(g, xz, d);
     fp2_add(h, e, f);
     fp2_sub(h, h, g);
     fp2_sub(h, h, g);               // H = E + F - 2G
     fp2_mul(l3, theta, xq);
     fp2_mul(u, lambda, yq);
     fp2_sub(l3, l3, u);
-    fp2_neg(u5, theta);
-    fp2_mul_xi(u, lambda);
+    fp2_mul(u, theta, zq);
+    fp2_neg(u5, u);
+    fp2_mul(u, lambda, zq);
+    fp2_mul_xi(u, u);
     fp2_neg(u0, u);
     fp2_mul(t.x, lambda, h);
     fp2_sub(u, g, h);
     fp2_mul(u, theta, u);
-    fp2_mul(g, e, t.y);
+    fp2_mul(g, e, yz);
     fp2_sub(t.y, u, g);
-    fp2_mul(t.z, t.z, e);
+    fp2_mul(t.z, zz, e);
+}
+// Start of a point chain from a Jacobian Q = (X : Y : Z), x = X/Z^2, y = Y/Z^3: homogeneous (X Z : Y : Z^3)
+template <class F2>
+B3_FN void miller_start(miller_pt_t<F2>& t, const F2& X, const F2& Y, const F2& Z) {
+    F2 z2;
+    fp2_sqr(z2, Z);
+    fp2_mul(t.x, X, Z);
+    t.y = Y;
+    fp2_mul(t.z, z2, Z);
 }
 // dense Fp12 value of a line  l0 + l3 w^3 + l5 w^5
 B3_FN void fp12_from_line(fp12& f, const fp2& l0, const fp2& l3, const fp2& l5) {

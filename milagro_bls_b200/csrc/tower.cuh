@@ -127,6 +127,57 @@ B3_FN_NOINLINE bool fp2_sqrt_or_z(fp2& r, const fp2& a) {
     return sq;
 }
 
+// Square root of a RATIO u / v in Fp2 (v != 0) with two Fp exponentiations and no inversion:
+//   r = sqrt(u / v)       and returns true   if u / v is a square in Fp2,
+//   r = sqrt(Z u / v)     and returns false  otherwise  (Z = SSWU_Z, N(Z) = 5).
+// Method: X = u / v = W / b with W = u conj(v), b = N(v) in Fp.  N(X) = N(W) / b^2, so  s = sqrt(N(X)) = t / b with
+// t = sqrt(N(W)) (first exponentiation; if N(W) is a non-residue switch to Z W, t <- sqrt(-5) t as in fp2_sqrt_or_z).
+// With D = (W0 + t) / 2 = b delta:  x0 = sqrt(delta) = sqrt(D / b) = D b g,  g = (D b^3)^((p-3)/4)  (second
+// exponentiation), chi = g^2 D b^3 = +-1, and 1 / (b x0) = chi g b, so the other coordinate W1 / (2 b x0) needs no
+// inversion either.  chi = -1 means x0^2 = -delta and the two coordinates swap roles (see fp2_sqrt_or_z).
+B3_FN_NOINLINE bool fp2_sqrt_ratio_or_z(fp2& r, const fp2& u, const fp2& v) {
+    fp b, n, t, tinv, s0;
+    fp2 W, cv;
+    fp_sqr(b, v.c0);
+    fp_sqr(s0, v.c1);
+    fp_add(b, b, s0);                                    // b = N(v)
+    fp2_conj(cv, v);
+    fp2_mul(W, u, cv);                                   // W = u conj(v)
+    fp_sqr(n, W.c0);
+    fp_sqr(s0, W.c1);
+    fp_add(n, n, s0);                                    // N(W)
+    bool sq = fp_sqrt_ratio_parts(t, tinv, n);           // t^2 = N(W) (sq) or -N(W) (!sq)
+    if (!sq) {
+        fp2_mul(W, W, SSWU_Z);                           // N(Z W) = 5 N(W), sqrt = sqrt(-5) t
+        fp_mul(t, t, FP_SQRT_M5);
+    }
+    fp D;
+    fp_add(D, W.c0, t);
+    fp_half(D, D);
+    if (fp_is_zero(D)) {                                 // W0 = -t: W1 = 0; use the conjugate branch
+        fp_sub(D, W.c0, t);
+        fp_half(D, D);
+    }
+    fp b2, b3, E, g, chi, x0, yv, hw1;
+    fp_sqr(b2, b);
+    fp_mul(b3, b2, b);
+    fp_mul(E, D, b3);
+    fp_pow_const(g, E, FP_EXP_SQRT_G);                   // g = E^((p-3)/4)
+    fp_mul(chi, g, E);
+    fp_mul(chi, chi, g);                                 // chi = E^((p-1)/2) in {0, 1, -1}
+    bool plus = !fp_eq(chi, FP_M_ONE);
+    fp_mul(x0, D, b);
+    fp_mul(x0, x0, g);                                   // x0 = D b g,  x0^2 = chi D / b
+    fp_half(hw1, W.c1);
+    fp_mul(yv, hw1, b);
+    fp_mul(yv, yv, g);                                   // (W1 / 2) b g
+    fp nyv;
+    fp_neg(nyv, yv);
+    if (plus) { r.c0 = x0; r.c1 = yv; }
+    else { r.c0 = nyv; r.c1 = x0; }
+    return sq;
+}
+
 // ---------------------------------------------------------------- Fp6
 B3_FN void fp6_add(fp6& r, const fp6& a, const fp6& b) { fp2_add(r.c0, a.c0, b.c0); fp2_add(r.c1, a.c1, b.c1); fp2_add(r.c2, a.c2, b.c2); }
 B3_FN void fp6_sub(fp6& r, const fp6& a, const fp6& b) { fp2_sub(r.c0, a.c0, b.c0); fp2_sub(r.c1, a.c1, b.c1); fp2_sub(r.c2, a.c2, b.c2); }

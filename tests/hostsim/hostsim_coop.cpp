@@ -51,17 +51,24 @@ int hc_multi_pairing_split(const uint8_t* q192s, const uint8_t* p96s, int n, uin
         if ((e = g2_aff_from_wire(Q, q192s + 192 * i))) return e;
         if ((e = g1_aff_from_wire(P, p96s + 96 * i))) return e;
         if (Q.inf || P.inf) continue;
-        miller_pt_t<fp2> t; t.x = Q.x; t.y = Q.y; fp2_one(t.z);
-        fp nyp; fp_neg(nyp, P.y);
+        // de-normalise both members (Jacobian with Z = 3 resp. 5) so the projective paths are exercised
+        fp three, five; fp_add(three, FP_ONE, FP_ONE); fp_add(three, three, FP_ONE); fp_add(five, three, FP_ONE); fp_add(five, five, FP_ONE);
+        fp2 qz; qz.c0 = three; qz.c1 = five;
+        fp2 qz2, qz3, qX, qY; fp2_sqr(qz2, qz); fp2_mul(qz3, qz2, qz); fp2_mul(qX, Q.x, qz2); fp2_mul(qY, Q.y, qz3);
+        fp pz2, pz3, pX, pY; fp_sqr(pz2, five); fp_mul(pz3, pz2, five); fp_mul(pX, P.x, pz2); fp_mul(pY, P.y, pz3);
+        fp pxz, pny; fp_mul(pxz, pX, five); fp_neg(pny, pY);                  // g1_pp: (X Z, -Y, Z^3)
+        miller_pt_t<fp2> t, Qh;
+        miller_start(t, qX, qY, qz);
+        Qh = t;
         int a = B3_MILLER_DBL_SLOTS;
         for (int it = 0; it < B3_MILLER_DBL_SLOTS; it++) {
             fp2 u0, l3, u5, l0, l5;
             miller_dbl_step_u(t, u0, l3, u5);
-            fp2_mul_fp(l0, u0, nyp); fp2_mul_fp(l5, u5, P.x);
+            fp2_mul_fp(l0, u0, pny); fp2_mul_fp(l3, l3, pz3); fp2_mul_fp(l5, u5, pxz);
             fp12_mul_by_line(slots[it], l0, l3, l5);
             if ((B3_X_ABS >> (62 - it)) & 1) {
-                miller_add_step_u(t, u0, l3, u5, Q.x, Q.y);
-                fp2_mul_fp(l0, u0, nyp); fp2_mul_fp(l5, u5, P.x);
+                miller_add_step_u(t, u0, l3, u5, Qh.x, Qh.y, Qh.z);
+                fp2_mul_fp(l0, u0, pny); fp2_mul_fp(l3, l3, pz3); fp2_mul_fp(l5, u5, pxz);
                 fp12 d; fp12_from_line(d, l0, l3, l5);
                 fp12_mul(slots[a], slots[a], d);
                 a++;
