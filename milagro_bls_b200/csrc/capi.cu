@@ -18,6 +18,7 @@ static const uint8_t kDstG2[] = "BLS_SIG_BLS12381G2_XMD:SHA-256_SSWU_RO_POP_";  
 static const size_t kDstG2Len = 43;
 
 #define B3_MAX_MARKS 24
+#define B3_MSM_MIN_SETS 512     // below this, S = sum [c_j] sig_j uses n separate ladders + a tree
 #define B3_N_STAGES 11
 // stage ids (b3_ctx_stage_ms / b3_stage_name)
 enum { ST_SIG_CHECK = 0, ST_AGGREGATE, ST_G1_MUL, ST_HASH_TO_G2, ST_G2_MUL_SUM, ST_MILLER, ST_FP12_PRODUCT, ST_FINAL_EXP, ST_COPY, ST_MILLER_LINES, ST_END };
@@ -599,8 +600,8 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
     CKR(ensure(ctx, ctx->ok, 4 * (n + 8)));
     CKR(ensure(ctx, ctx->g1j, sizeof(g1_jac) * (n + 1)));
     CKR(ensure(ctx, ctx->g1j2, sizeof(g1_jac) * (n + 1)));
-    CKR(ensure(ctx, ctx->g1pp, sizeof(g1_pp) * (n + 1)));
-    CKR(ensure(ctx, ctx->g2q, sizeof(g2_jac) * (n + 1)));
+    CKR(ensure(ctx, ctx->g1pp, sizeof(g1_pp) * (n + B3_MSM_WINDOWS)));
+    CKR(ensure(ctx, ctx->g2q, sizeof(g2_jac) * (n + B3_MSM_WINDOWS)));
     CKR(ensure(ctx, ctx->g2j2, sizeof(g2_jac) * (n + 2)));
     CKR(ensure(ctx, ctx->misc, 64));
     int32_t* d_st_sig = (int32_t*)ctx->status.p;
@@ -648,7 +649,6 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
         span_end(ctx, sp, s1);
         sp = span_begin(ctx, ST_G1_MUL, s1);
         LAUNCH_ON(s1, k_g1_mul_u64_pp, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j.p, d_scalars, n, p);
-        LAUNCH_ON(s1, k_set_neg_g1_pp, 1, 1, p + n);
         span_end(ctx, sp, s1);
         // 4. H_j = hash_to_curve_g2(msg_j), affine (M/src/aggregates.rs:290,296)
         sp = span_begin(ctx, ST_HASH_TO_G2, s2);
@@ -656,10 +656,22 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
         span_end(ctx, sp, s2);
         // 5. S = sum_j [c_j] sig_j (M/src/aggregates.rs:303)
         sp = span_begin(ctx, ST_G2_MUL_SUM, sm);
-        LAUNCH_ON(sm, k_g2_mul_u64, nblk(2 * n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, d_scalars, n, (g2_jac*)ctx->g2j.p);
-        g2_jac* s;
-        CKR(g2_sum(ctx, (g2_jac*)ctx->g2j.p, (g2_jac*)ctx->g2j2.p, n, &s));
-        CK(cudaMemcpyAsync(q + n, s, sizeof(g2_jac), cudaMemcpyDeviceToDevice, sm));
+        if (n >= B3_MSM_MIN_SETS) {           // bucket method: 8 window sums, each its own pair against -[2^(8w)] G1
+            const size_t nb = (size_t)B3_MSM_WINDOWS * B3_MSM_BUCKETS;
+            CKR(ensure(ctx, ctx->g2j, sizeof(g2_jac) * nb * B3_MSM_SEGS));
+            CKR(ensure(ctx, ctx->g2j2, sizeof(g2_jac) * B3_MSM_WINDOWS * 256));
+            LAUNCH_ON(sm, k_msm_bucket, nblk(2 * nb * B3_MSM_SEGS), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, d_scalars, n, (g2_jac*)ctx->g2j.p);
+            LAUNCH_ON(sm, k_msm_scale, nblk(2 * B3_MSM_WINDOWS * 256), B3_TPB, (const g2_jac*)ctx->g2j.p, (g2_jac*)ctx->g2j2.p);
+            LAUNCH_ON(sm, k_msm_window_sum, B3_MSM_WINDOWS, 512, (g2_jac*)ctx->g2j2.p);
+            LAUNCH_ON(sm, k_msm_pairs, 1, 32, (const g2_jac*)ctx->g2j2.p, q + n, p + n);
+        } else {
+            g2_jac* s;
+            CKR(ensure(ctx, ctx->g2j, sizeof(g2_jac) * (n + 1)));
+            LAUNCH_ON(sm, k_g2_mul_u64, nblk(2 * n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, d_scalars, n, (g2_jac*)ctx->g2j.p);
+            CKR(g2_sum(ctx, (g2_jac*)ctx->g2j.p, (g2_jac*)ctx->g2j2.p, n, &s));
+            CK(cudaMemcpyAsync(q + n, s, sizeof(g2_jac), cudaMemcpyDeviceToDevice, sm));
+            LAUNCH_ON(sm, k_set_neg_g1_pp, 1, 1, p + n);
+        }
         span_end(ctx, sp, sm);
         if (!ctx->serial) {
             cudaStream_t auxs[3] = {s0, s1, s2};
@@ -670,7 +682,7 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
         }
     }
     // 6. Miller loops over the n + 1 pairs, product
-    CKR(miller_product(ctx, q, p, n ? n + 1 : 0, res));
+    CKR(miller_product(ctx, q, p, n == 0 ? 0 : n + (n >= B3_MSM_MIN_SETS ? B3_MSM_WINDOWS : 1), res));
     *d_first_bad_out = d_first_bad;
     // wire-format errors of the inputs (cannot happen for values that came out of the reference's own types)
     *parse_err = B3_OK;

@@ -184,6 +184,10 @@ out.append(fp_c("FP_SQRT_M5", SQRT_M5))
 out.append(fp_c("G1_GEN_X", G1X))
 out.append(fp_c("G1_GEN_Y", G1Y))
 out.append(fp_c("G1_GEN_NEG_Y", (-G1Y) % p))
+# [2^(8w)] G1, w = 0..7: G1 members of the per-window pairs of the bucket-method sum (kernels.cuh, k_msm_*)
+_pow = [g1_mul((G1X, G1Y), 1 << (8 * w)) for w in range(8)]
+out.append(fp_arr("G1_POW256_X", [P[0] for P in _pow]))
+out.append(fp_arr("G1_POW256_Y", [P[1] for P in _pow]))
 out.append(fp2_c("G2_GEN_X", G2X))
 out.append(fp2_c("G2_GEN_Y", G2Y))
 out.append(fp2_arr("FROB_GAMMA1", GAMMA1))

@@ -408,6 +408,34 @@ def test_verify_multiple_medium_batch(eng):
     assert not ok and fb == -1
 
 
+def test_verify_multiple_large_batch_vs_c_oracle(eng):
+    """640 sets x 2 keys: large enough for the bucket-method path of S = sum [c_j] sig_j and for several accumulating
+    threads per Miller slot.  Accept on valid input (GT = one) and, after one flipped message bit, a GT value that is
+    NOT one and must equal the C oracle's bytes (oracle/bls_oracle_c.c, the reference's per-set algorithm)."""
+    from oracle import c_oracle
+    from milagro_bls_b200 import SeededRng, draw_scalar
+    rnd = random.Random(11)
+    n_sets, n_keys = 640, 2
+    sks = [rnd.randrange(1, O.r) for _ in range(n_sets * n_keys)]
+    pk = eng.g1_mul_gen(sks)
+    msgs = [bytes(rnd.getrandbits(8) for _ in range(32)) for _ in range(n_sets)]
+    H = eng.hash_to_g2(msgs)
+    agg_sk = [sum(sks[j * n_keys:(j + 1) * n_keys]) % O.r for j in range(n_sets)]
+    sig = eng.g2_mul(H.reshape(-1), agg_sk)
+    rng = SeededRng(b"large-batch")
+    scalars = np.array([draw_scalar(rng) for _ in range(n_sets)], dtype=np.uint64)
+    scalars[0] = 1
+    scalars[1] = (1 << 63) - 1                                     # extreme scalars of the draw rule
+    offs = list(range(0, n_sets * n_keys + 1, n_keys))
+    moff = list(range(0, 32 * n_sets + 1, 32))
+    ok, fb, gt = eng.verify_multiple(sig.reshape(-1), pk.reshape(-1), offs, b"".join(msgs), moff, scalars, want_gt=True)
+    assert ok and fb == -1 and gt == O.f12_to_bytes(O.F12_ONE)
+    flipped = bytearray(b"".join(msgs)); flipped[32 * 333 + 9] ^= 0x10
+    ok, fb, gt = eng.verify_multiple(sig.reshape(-1), pk.reshape(-1), offs, bytes(flipped), moff, scalars, want_gt=True)
+    ok_c, gt_c = c_oracle.verify_multiple(sig.reshape(-1), pk.reshape(-1), offs, bytes(flipped), moff, scalars)
+    assert not ok and not ok_c and fb == -1 and gt == gt_c and gt != O.f12_to_bytes(O.F12_ONE)
+
+
 def test_imad_probe_runs(eng):
     assert eng.imad_peak(False) > 1e12
     assert eng.imad_peak(True) > 1e11
