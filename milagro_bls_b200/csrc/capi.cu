@@ -103,8 +103,11 @@ extern "C" int b3_ctx_create(int device, b3_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B3_ERR_CUDA; }
     for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
     for (int i = 0; i < B3_MAX_MARKS; i++) { cudaEventCreate(&ctx->span_a[i]); cudaEventCreate(&ctx->span_b[i]); }
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     for (int i = 0; i < 3; i++) {
-        if (cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B3_ERR_CUDA; }
+        // aux[2] carries the longest dependent chain of a batch (hash_to_G2 -> Miller point chains): highest priority
+        if (cudaStreamCreateWithPriority(&ctx->aux[i], cudaStreamNonBlocking, i == 2 ? prio_hi : prio_lo) != cudaSuccess) { delete ctx; return B3_ERR_CUDA; }
         cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
@@ -206,9 +209,22 @@ static int g2_sum(b3_ctx* ctx, g2_jac* a, g2_jac* b, size_t n, g2_jac** res) {
     *res = src;
     return B3_OK;
 }
-// Miller loops over n_pairs (q[i], p[i]) -> product left in *res.  Split multi-Miller loop (pairing.cuh):
-// point chains -> lines in HBM (68 x n x 288 B), per-slot accumulation over all pairs, one cooperative closing chain.
-static int miller_product(b3_ctx* ctx, const g2_jac* q, const g1_pp* p, size_t n_pairs, fp12** res) {
+// Split multi-Miller loop (pairing.cuh), step 1: point chains of pairs [first, first + count) of an n_pairs product
+// -> lines in HBM (68 x n_pairs x 288 B).  May be issued on any stream as soon as those q's exist.
+static int miller_lines(b3_ctx* ctx, cudaStream_t strm, const g2_jac* q, size_t n_pairs, size_t first, size_t count) {
+    if (count == 0) return B3_OK;
+    int sp = span_begin(ctx, ST_MILLER_LINES, strm);
+    LAUNCH_ON(strm, k_miller_lines, nblk(2 * count), B3_TPB, q, n_pairs, first, count, (fp2*)ctx->lines.p, (uint32_t*)ctx->qinf.p);
+    span_end(ctx, sp, strm);
+    return B3_OK;
+}
+static int miller_reserve(b3_ctx* ctx, size_t n_pairs) {
+    CKR(ensure(ctx, ctx->lines, sizeof(fp2) * 3 * B3_MILLER_SLOTS * (n_pairs ? n_pairs : 1)));
+    CKR(ensure(ctx, ctx->qinf, 4 * (n_pairs ? n_pairs : 1)));
+    return B3_OK;
+}
+// steps 2 and 3 (context stream): per-slot accumulation over all pairs, one cooperative closing chain -> *res
+static int miller_finish(b3_ctx* ctx, const g1_pp* p, size_t n_pairs, fp12** res) {
     size_t chunks = (n_pairs + 1024) / 2048;              // ~16 pairs per accumulating thread
     if (chunks < 1) chunks = 1;
     if (chunks > 64) chunks = 64;
@@ -222,16 +238,9 @@ static int miller_product(b3_ctx* ctx, const g2_jac* q, const g1_pp* p, size_t n
         LAUNCH(k_fp12_set_one, 1, 1, out);
         return B3_OK;
     }
-    CKR(ensure(ctx, ctx->lines, sizeof(fp2) * 3 * B3_MILLER_SLOTS * n_pairs));
-    CKR(ensure(ctx, ctx->qinf, 4 * n_pairs));
-    fp2* lines = (fp2*)ctx->lines.p;
-    uint32_t* qinf = (uint32_t*)ctx->qinf.p;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-    int sp = span_begin(ctx, ST_MILLER_LINES, ctx->stream);
-    LAUNCH(k_miller_lines, nblk(2 * n_pairs), B3_TPB, q, n_pairs, lines, qinf);
-    span_end(ctx, sp, ctx->stream);
-    sp = span_begin(ctx, ST_MILLER, ctx->stream);
-    LAUNCH(k_miller_accum, dim3((unsigned)chunks, B3_MILLER_SLOTS), B3_TPB, (const fp2*)lines, (const uint32_t*)qinf, p, n_pairs, K, partial);
+    int sp = span_begin(ctx, ST_MILLER, ctx->stream);
+    LAUNCH(k_miller_accum, dim3((unsigned)chunks, B3_MILLER_SLOTS), B3_TPB, (const fp2*)ctx->lines.p, (const uint32_t*)ctx->qinf.p, p, n_pairs, K, partial);
     span_end(ctx, sp, ctx->stream);
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     sp = span_begin(ctx, ST_FP12_PRODUCT, ctx->stream);
@@ -243,6 +252,12 @@ static int miller_product(b3_ctx* ctx, const g2_jac* q, const g1_pp* p, size_t n
     }
     span_end(ctx, sp, ctx->stream);
     return B3_OK;
+}
+// whole product on the context stream
+static int miller_product(b3_ctx* ctx, const g2_jac* q, const g1_pp* p, size_t n_pairs, fp12** res) {
+    CKR(miller_reserve(ctx, n_pairs));
+    CKR(miller_lines(ctx, ctx->stream, q, n_pairs, 0, n_pairs));
+    return miller_finish(ctx, p, n_pairs, res);
 }
 // final exponentiation of *m -> accept / gt on the host
 static int finish(b3_ctx* ctx, const fp12* m, int* accept, uint8_t* gt576) {
@@ -611,6 +626,8 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
     CK(cudaMemcpyAsync(d_first_bad, &init, 8, cudaMemcpyHostToDevice, ctx->stream));
     g2_jac* q = (g2_jac*)ctx->g2q.p;
     g1_pp* p = (g1_pp*)ctx->g1pp.p;
+    const size_t n_total = n == 0 ? 0 : n + (n >= B3_MSM_MIN_SETS ? B3_MSM_WINDOWS : 1);
+    CKR(miller_reserve(ctx, n_total));
     if (n > 0) {
         CKR(ensure(ctx, ctx->g2j, sizeof(g2_jac) * (n + 1)));
         // The four stages below are independent of each other; unless ctx->serial they run concurrently:
@@ -624,6 +641,12 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
             CK(cudaStreamWaitEvent(s1, ctx->ev_fork, 0));
             CK(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
         }
+        // 4. H_j = hash_to_curve_g2(msg_j) (M/src/aggregates.rs:290) and its Miller point chain: the longest dependent chain of
+        //    the batch, so it is issued FIRST (blocks are dispatched in launch order) on the high-priority stream
+        sp = span_begin(ctx, ST_HASH_TO_G2, s2);
+        CKR(hash_to_g2_jac_dev(ctx, s2, d_msgs, d_msg_off, n, q));
+        span_end(ctx, sp, s2);
+        CKR(miller_lines(ctx, s2, q, n_total, 0, n));                 // the point chains need only H_j
         // 1. signatures: parse + on-curve (main), subgroup check (M/src/aggregates.rs:274-276) on aux0
         sp = span_begin(ctx, ST_COPY, sm);
         LAUNCH_ON(sm, k_g2_parse, nblk(n), B3_TPB, d_sigs, n, (g2_aff*)ctx->g2a_sig.p, d_st_sig, 1);
@@ -650,10 +673,6 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
         sp = span_begin(ctx, ST_G1_MUL, s1);
         LAUNCH_ON(s1, k_g1_mul_u64_pp, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j.p, d_scalars, n, p);
         span_end(ctx, sp, s1);
-        // 4. H_j = hash_to_curve_g2(msg_j), affine (M/src/aggregates.rs:290,296)
-        sp = span_begin(ctx, ST_HASH_TO_G2, s2);
-        CKR(hash_to_g2_jac_dev(ctx, s2, d_msgs, d_msg_off, n, q));
-        span_end(ctx, sp, s2);
         // 5. S = sum_j [c_j] sig_j (M/src/aggregates.rs:303)
         sp = span_begin(ctx, ST_G2_MUL_SUM, sm);
         if (n >= B3_MSM_MIN_SETS) {           // bucket method: 8 window sums, each its own pair against -[2^(8w)] G1
@@ -673,6 +692,7 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
             LAUNCH_ON(sm, k_set_neg_g1_pp, 1, 1, p + n);
         }
         span_end(ctx, sp, sm);
+        CKR(miller_lines(ctx, sm, q, n_total, n, n_total - n));       // ... and the window sums / S
         if (!ctx->serial) {
             cudaStream_t auxs[3] = {s0, s1, s2};
             for (int k = 0; k < 3; k++) {
@@ -682,7 +702,7 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
         }
     }
     // 6. Miller loops over the n + 1 pairs, product
-    CKR(miller_product(ctx, q, p, n == 0 ? 0 : n + (n >= B3_MSM_MIN_SETS ? B3_MSM_WINDOWS : 1), res));
+    CKR(miller_finish(ctx, p, n_total, res));
     *d_first_bad_out = d_first_bad;
     // wire-format errors of the inputs (cannot happen for values that came out of the reference's own types)
     *parse_err = B3_OK;

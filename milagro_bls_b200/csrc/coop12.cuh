@@ -3,9 +3,10 @@
 // Used where the path is a single long dependent chain of Fp12 operations with nothing else to run beside it:
 // the final exponentiation (A/pair.rs:409-541) and the closing sqr/mul chain of the multi-Miller loop
 // (A/pair.rs:166-178).  An Fp12 product is done schoolbook over the six Fp2 coefficients of the w-power basis
-// (w^6 = xi): 36 Fp2 products = 108 Fp products (Karatsuba inside each Fp2 product), ONE Fp product per thread,
-// then 12 threads assemble the 12 output coordinates.  Latency of an Fp12 multiplication or squaring is therefore
-// about two Fp-multiplication latencies instead of 54 (18 for a cyclotomic squaring) on one thread.
+// (w^6 = xi): 36 Fp2 products, each coordinate of each product ONE dual Montgomery product (fp_mul2) on its own
+// thread (72 threads), then 12 threads add up the six terms of the 12 output coordinates.  Latency of an Fp12
+// multiplication or squaring is therefore about 1.5 Fp-multiplication latencies plus five additions, instead of 54
+// multiplications (18 for a cyclotomic squaring) on one thread.
 //
 // Every routine is written as per-thread "phase" functions taking an explicit thread index, with a CTA barrier
 // between phases, so tests/hostsim can replay the phases sequentially on the CPU.
@@ -15,7 +16,7 @@
 #define B3_COOP_THREADS 128
 
 struct coop_ws {
-    fp prod[108];
+    fp val[72];
 };
 
 // w-power k (0..5) -> index of that Fp2 coefficient in the memory order of fp12 (c0.c0,c0.c1,c0.c2,c1.c0,c1.c1,c1.c2)
@@ -24,41 +25,37 @@ B3_FN const fp2& coop_coef(const fp12& a, int k) { return reinterpret_cast<const
 B3_FN fp2& coop_coef(fp12& a, int k) { return reinterpret_cast<fp2*>(&a)[coop_slot(k)]; }
 
 // ---- r = a * b --------------------------------------------------------------------------------
-// phase 1: thread tid < 108 computes one of the three Karatsuba products of a_i * b_j
+// r_k = sum_{i+j=k} a_i b_j + xi sum_{i+j=k+6} a_i b_j   (k = 0..5, Fp2 coefficients of w^k).
+// phase 1: thread tid < 72 = (output coordinate c = 2k + comp, term i) computes ONE coordinate of ONE term
+//   a_i * B,  B = b_j (i + j = k)  or  xi b_j (i + j = k + 6),  as a dual product with a single reduction:
+//   comp 0:  a_i0 B0 + (-a_i1) B1        comp 1:  a_i0 B1 + a_i1 B0
 B3_FN void coop_mul_p1(coop_ws& ws, const fp12& a, const fp12& b, int tid) {
-    if (tid >= 108) return;
-    int pr = tid / 3, k = tid - 3 * pr, i = pr / 6, j = pr - 6 * i;
+    if (tid >= 72) return;
+    const int c = tid / 6, i = tid - 6 * c, k = c >> 1, comp = c & 1;
+    int j = k - i;
+    const bool wrap = j < 0;
+    if (wrap) j += 6;
     const fp2& x = coop_coef(a, i);
     const fp2& y = coop_coef(b, j);
-    fp u, v;
-    if (k == 0) { u = x.c0; v = y.c0; }
-    else if (k == 1) { u = x.c1; v = y.c1; }
-    else { fp_add(u, x.c0, x.c1); fp_add(v, y.c0, y.c1); }
-    fp_mul(ws.prod[tid], u, v);
+    fp B0 = y.c0, B1 = y.c1;
+    if (wrap) {                                    // xi (y0 + y1 i) = (y0 - y1) + (y0 + y1) i
+        fp_sub(B0, y.c0, y.c1);
+        fp_add(B1, y.c0, y.c1);
+    }
+    fp u2, v1, v2;
+    fp_neg(u2, x.c1);
+    fp_select(u2, comp != 0, x.c1, u2);
+    fp_select(v1, comp != 0, B1, B0);
+    fp_select(v2, comp != 0, B0, B1);
+    fp_mul2(ws.val[tid], x.c0, v1, u2, v2);
 }
-// phase 2: thread tid < 12 assembles one Fp coordinate of r.  With (p0, p1, p2) the products of (a_i, b_j):
-//   a_i b_j = t0 + t1 i,  t0 = p0 - p1,  t1 = p2 - p0 - p1;   xi (t0 + t1 i) = (2 p0 - p2) + (p2 - 2 p1) i
+// phase 2: thread tid < 12 sums the six terms of one output coordinate
 B3_FN void coop_mul_p2(fp12& r, const coop_ws& ws, int tid) {
     if (tid >= 12) return;
-    int k = tid >> 1, comp = tid & 1;
-    fp acc = FP_NIL;
-    for (int i = 0; i < 6; i++) {
-        int j = k - i;
-        bool wrap = j < 0;
-        if (wrap) j += 6;
-        const fp* p = &ws.prod[(i * 6 + j) * 3];
-        fp t;
-        if (!comp) {
-            if (!wrap) fp_sub(t, p[0], p[1]);
-            else { fp_dbl(t, p[0]); fp_sub(t, t, p[2]); }
-        } else {
-            if (!wrap) { fp_sub(t, p[2], p[0]); fp_sub(t, t, p[1]); }
-            else { fp_dbl(t, p[1]); fp_sub(t, p[2], t); }
-        }
-        fp_add(acc, acc, t);
-    }
-    fp2& o = coop_coef(r, k);
-    if (comp) o.c1 = acc; else o.c0 = acc;
+    fp acc = ws.val[6 * tid];
+    for (int i = 1; i < 6; i++) fp_add(acc, acc, ws.val[6 * tid + i]);
+    fp2& o = coop_coef(r, tid >> 1);
+    if (tid & 1) o.c1 = acc; else o.c0 = acc;
 }
 // ---- r = conj(a) (w -> -w): odd w-powers negated -----------------------------------------------------------
 B3_FN void coop_conj_p(fp12& r, const fp12& a, int tid) {

@@ -557,9 +557,12 @@ __global__ void __launch_bounds__(B3_TPB) k_g2_aff_to_jac(const g2_aff* in, size
 // ---- split multi-Miller loop (pairing.cuh: "split Miller loop") ---------------------------------------------------
 // 1. point chain of every pair -> unscaled lines, lines[(slot * n + pair) * 3 + {0,1,2}] = (u0, l3, u5)
 //    LANE PAIRS: threads (2i, 2i+1) run the chain of pair i, each storing its half of every coefficient.
-__global__ void __launch_bounds__(B3_TPB) k_miller_lines(const g2_jac* __restrict__ q, size_t n, fp2* __restrict__ lines, uint32_t* __restrict__ qinf) {
+//    Pairs [first, first + count) of the n pairs of the product (different ranges may run on different streams).
+__global__ void __launch_bounds__(B3_TPB) k_miller_lines(const g2_jac* __restrict__ q, size_t n, size_t first, size_t count,
+                                                         fp2* __restrict__ lines, uint32_t* __restrict__ qinf) {
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
-    if (i >= n) return;
+    if (i >= count) return;
+    i += first;
     fp2h X, Y, Z;
     fp2h_load(X, q[i].x);
     fp2h_load(Y, q[i].y);
