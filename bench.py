@@ -141,7 +141,7 @@ def reference_main(args):
     sample = max(cores, args.ref_sets)
     times, last = [], None
     for it in range(args.warmup + args.steps):
-        last = cpu_reference_run(sample, KEYS_PER_SET, 0xB200 + it, cores)
+        last = cpu_reference_run(sample, KEYS_PER_SET, 0xB200, cores)
         if it >= args.warmup:
             times.append(last["seconds"])
     sec = sum(times) / max(len(times), 1)
@@ -168,7 +168,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--sets", type=int, default=SETS_PER_GPU, help="sets per GPU (default: the C4 shape)")
     ap.add_argument("--keys", type=int, default=KEYS_PER_SET)
-    ap.add_argument("--ref-sets", type=int, default=64, help="sets per step of the CPU reference arm / cpu_baseline sample")
+    ap.add_argument("--ref-sets", type=int, default=2048,
+                    help="sets per step of the CPU reference arm / cpu_baseline sample (~20 s of CPU work on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print the per-stage device times to stderr")
     args = ap.parse_args()
@@ -179,6 +180,7 @@ def main():
     import torch
     import torch.distributed as dist
     import milagro_bls_b200 as mb
+    from milagro_bls_b200 import sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -203,7 +205,6 @@ def main():
     d = {k: torch.from_numpy(inp[k]).to(dev) for k in ("sigs", "pks", "pk_off", "msgs", "msg_off")}
     d["scal"] = torch.from_numpy(scal.view(np.int64)).to(dev)
     partial = torch.zeros(mb._lib.PARTIAL_BYTES, dtype=torch.uint8, device=dev)
-    gathered = torch.zeros(world * mb._lib.PARTIAL_BYTES, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
     base = rank * n
 
@@ -220,9 +221,9 @@ def main():
                                         d["msg_off"].data_ptr(), d["scal"].data_ptr(), n, base, partial.data_ptr())
         add_stages()
         if world > 1:
-            dist.all_gather_into_tensor(gathered, partial)
+            g = sharding.all_gather_partials(partial, world)          # the ONLY collective: world x 592 bytes over NCCL
             torch.cuda.current_stream().synchronize()
-            r = eng.combine_partials_dev(gathered.data_ptr(), world)
+            r = eng.combine_partials_dev(g.data_ptr(), world)
         else:
             r = eng.combine_partials_dev(partial.data_ptr(), 1)
         add_stages()
@@ -245,9 +246,9 @@ def main():
         torch.cuda.current_stream().synchronize()
         eng.verify_multiple_partial_dev(d["sigs"].data_ptr(), d["pks"].data_ptr(), d["pk_off"].data_ptr(), d["msgs"].data_ptr(),
                                         d["msg_off"].data_ptr(), d["scal"].data_ptr(), n, base, partial.data_ptr())
-        dist.all_gather_into_tensor(gathered, partial)
+        g = sharding.all_gather_partials(partial, world)
         torch.cuda.current_stream().synchronize()
-        return eng.combine_partials_dev(gathered.data_ptr(), world)
+        return eng.combine_partials_dev(g.data_ptr(), world)
 
     def barrier():
         torch.cuda.synchronize()
@@ -299,6 +300,20 @@ def main():
         ok_bad, _ = eng.combine_partials_dev(partial.data_ptr(), 1)
         assert not ok_bad, "tampered batch must reject"
 
+    # second headline metric: hash_to_G2/s (b3_hash_to_g2_dev: SHA-256 xmd, SSWU, 3-isogeny, cofactor clearing, affine
+    # normalisation and 192-byte wire output), 32-byte messages resident in HBM
+    nh = 16384
+    hm = torch.from_numpy(np.random.RandomState(5 + rank).randint(0, 256, size=nh * MSG_LEN, dtype=np.uint8)).to(dev)
+    ho = torch.arange(0, nh * MSG_LEN + 1, MSG_LEN, dtype=torch.int32, device=dev)
+    hout = torch.empty(nh * 192, dtype=torch.uint8, device=dev)
+
+    def step_h2c():
+        eng.hash_to_g2_dev(hm.data_ptr(), ho.data_ptr(), nh, hout.data_ptr())
+        return (True, -1)
+
+    ms_h2c, _, _, _ = timed(step_h2c, args.steps, 2)
+    h2c_rate = nh * world * args.steps / (ms_h2c * 1e-3)
+
     total_sets = n * world
     value = total_sets * args.steps / (ms_res * 1e-3)
     e2e = total_sets * args.steps / (ms_e2e * 1e-3)
@@ -334,6 +349,7 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             try:
+                cpu_reference_run(max(os.cpu_count() or 1, args.ref_sets), nk, 0xB200, os.cpu_count() or 1)      # warm-up pass
                 c = cpu_reference_run(max(os.cpu_count() or 1, args.ref_sets), nk, 0xB200, os.cpu_count() or 1)
                 cpu = {"value": c["sets"] / c["seconds"], "unit": "sets/s", "cores": c["threads"], "kind": c["kind"],
                        "sample": f"{c['sets']} sets x {nk} keys, {c['threads']} independent single-threaded instances, {c['seconds']:.1f} s"}
@@ -349,6 +365,9 @@ def main():
                           "cache": "L2 flushed (256 MiB write) before every step; inputs ~103 MB per GPU"},
                "e2e": {"value": e2e, "unit": "sets/s", "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": (576 + 16) * world,
                        "ms_per_step": ms_e2e / args.steps},
+               "hash_to_g2": {"value": h2c_rate, "unit": "hash_to_G2/s", "messages_per_gpu": nh, "message_bytes": MSG_LEN,
+                              "ms_per_batch": ms_h2c / args.steps,
+                              "imad_frac": h2c_rate / world * FP_MULS["hash_to_g2_affine"] * MACS_PER_FP_MUL / peak_mac},
                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                "accept": bool(last[0])}
         if args.breakdown:
