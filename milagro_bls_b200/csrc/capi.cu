@@ -225,7 +225,9 @@ static int miller_reserve(b3_ctx* ctx, size_t n_pairs) {
 }
 // steps 2 and 3 (context stream): per-slot accumulation over all pairs, one cooperative closing chain -> *res
 static int miller_finish(b3_ctx* ctx, const g1_pp* p, size_t n_pairs, fp12** res) {
-    size_t chunks = (n_pairs + 1024) / 2048;              // ~16 pairs per accumulating thread
+    const char* ek = getenv("B3_ACC_K");
+    size_t kk = ek ? (size_t)atoi(ek) : 16;
+    size_t chunks = (n_pairs + 64 * kk) / (128 * kk);              // ~16 pairs per accumulating thread
     if (chunks < 1) chunks = 1;
     if (chunks > 64) chunks = 64;
     unsigned K = (unsigned)((n_pairs + chunks * B3_TPB - 1) / (chunks * B3_TPB));
@@ -240,7 +242,11 @@ static int miller_finish(b3_ctx* ctx, const g1_pp* p, size_t n_pairs, fp12** res
     }
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     int sp = span_begin(ctx, ST_MILLER, ctx->stream);
-    LAUNCH(k_miller_accum, dim3((unsigned)chunks, B3_MILLER_SLOTS), B3_TPB, (const fp2*)ctx->lines.p, (const uint32_t*)ctx->qinf.p, p, n_pairs, K, partial);
+    const char* elb = getenv("B3_ACC_LB");
+    int lb = elb ? atoi(elb) : 1;
+    if (lb == 3) LAUNCH(k_miller_accum<3>, dim3((unsigned)chunks, B3_MILLER_SLOTS), B3_TPB, (const fp2*)ctx->lines.p, (const uint32_t*)ctx->qinf.p, p, n_pairs, K, partial);
+    else if (lb == 4) LAUNCH(k_miller_accum<4>, dim3((unsigned)chunks, B3_MILLER_SLOTS), B3_TPB, (const fp2*)ctx->lines.p, (const uint32_t*)ctx->qinf.p, p, n_pairs, K, partial);
+    else LAUNCH(k_miller_accum<1>, dim3((unsigned)chunks, B3_MILLER_SLOTS), B3_TPB, (const fp2*)ctx->lines.p, (const uint32_t*)ctx->qinf.p, p, n_pairs, K, partial);
     span_end(ctx, sp, ctx->stream);
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     sp = span_begin(ctx, ST_FP12_PRODUCT, ctx->stream);
@@ -609,7 +615,7 @@ extern "C" int b3_aggregate_verify(b3_ctx* ctx, const uint8_t sig192[192], const
 // core of verify_multiple on device-resident inputs; leaves this rank's Miller product in *res and the first bad index in d_first_bad
 static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_t* d_pks, const uint32_t* d_pk_off, size_t total_keys,
                                 const uint8_t* d_msgs, const uint32_t* d_msg_off, const uint64_t* d_scalars, size_t n, long long index_base,
-                                fp12** res, long long** d_first_bad_out, int* parse_err) {
+                                fp12** res, long long** d_first_bad_out, int* parse_err, const uint8_t* h_pks = nullptr) {
     CKR(ensure(ctx, ctx->g2a_sig, sizeof(g2_aff) * (n + 1)));
     CKR(ensure(ctx, ctx->status, 4 * (2 * n + 8)));
     CKR(ensure(ctx, ctx->ok, 4 * (n + 8)));
@@ -660,6 +666,9 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
         LAUNCH_ON(s0, k_first_bad, nblk(n), B3_TPB, (const int32_t*)ctx->ok.p, n, index_base, d_first_bad);
         span_end(ctx, sp, s0);
         // 2. aggregate public keys; 3. P_j = [c_j] apk_j (M/src/aggregates.rs:293), affine
+        // host-pointer entry: the public keys (96 % of the input bytes) are copied on THIS stream, so the transfer
+        // overlaps hash_to_G2 and the signature work instead of preceding them
+        if (h_pks) CK(cudaMemcpyAsync((void*)d_pks, h_pks, 96 * total_keys, cudaMemcpyHostToDevice, s1));
         sp = span_begin(ctx, ST_AGGREGATE, s1);
         if (d_pk_off) {
             size_t avg = total_keys / n;
@@ -729,7 +738,7 @@ extern "C" int b3_verify_multiple(b3_ctx* ctx, const uint8_t* sigs192, const uin
     size_t total_keys = pk_off ? pk_off[n] : n;
     if (n) {
         CKR(h2d(ctx, ctx->in_a, sigs192, 192 * n));
-        CKR(h2d(ctx, ctx->in_b, pks96, 96 * total_keys));
+        CKR(ensure(ctx, ctx->in_b, 96 * total_keys + 1));             // copied inside the core, on the aggregation stream
         if (pk_off) CKR(h2d(ctx, ctx->in_e, pk_off, 4 * (n + 1)));
         CKR(h2d(ctx, ctx->in_c, msgs, msg_off[n]));
         CKR(h2d(ctx, ctx->in_d, msg_off, 4 * (n + 1)));
@@ -740,7 +749,7 @@ extern "C" int b3_verify_multiple(b3_ctx* ctx, const uint8_t* sigs192, const uin
     int perr;
     CKR(verify_multiple_core(ctx, (const uint8_t*)ctx->in_a.p, (const uint8_t*)ctx->in_b.p, pk_off ? (const uint32_t*)ctx->in_e.p : nullptr,
                              total_keys, (const uint8_t*)ctx->in_c.p, (const uint32_t*)ctx->in_d.p, (const uint64_t*)ctx->in_f.p, n, 0, &res,
-                             &d_fb, &perr));
+                             &d_fb, &perr, pks96));
     if (perr) return perr;
     int ok = 0;
     CKR(finish(ctx, res, &ok, gt576));

@@ -271,6 +271,54 @@ B3_FN void fp_mul2_inl(fp& r, const fp& a1, const fp& b1, const fp& a2, const fp
     even[11] = addc(even[11], 0);
     fp_final_sub(r, even);
 }
+// Six-term dot product with ONE reduction:  r = (sum_{t<6} a[t] * b[t]) / 2^384 mod p     (all operands < p)
+// 6 x 144 + 156 = 1020 multiply-accumulates instead of 6 x 300 plus five additions.  Running value < 7p(1 + 2^-32)
+// < 2^384 and result < p(1 + 6p/2^384) < 1.61p, so the accumulators and the single final subtraction carry over
+// from fp_mul_inl.  Operands are read through pointers (they live in local/shared memory: Fp12 accumulators).
+struct fp_dot6_args {
+    const fp* a[6];
+    const fp* b[6];
+};
+B3_FN_NOINLINE void fp_dot6(fp& r, fp_dot6_args q) {
+    uint32_t even[12], odd[12], av[6][12];
+#pragma unroll
+    for (int t = 0; t < 6; t++) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) av[t][i] = q.a[t]->l[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        uint32_t* E = (i & 1) ? odd : even;
+        uint32_t* O = (i & 1) ? even : odd;
+        uint32_t bi = q.b[0]->l[i];
+        if (i == 0) {
+            b3_mul_row(O, av[0] + 1, bi);
+            b3_mul_row(E, av[0], bi);
+        } else {
+            E[0] = add_cc(E[0], O[1]);
+            b3_mad_row_shift(O, av[0] + 1, bi);
+            b3_mad_row(E, av[0], bi);
+            O[11] = addc(O[11], 0);
+        }
+#pragma unroll
+        for (int t = 1; t < 6; t++) {
+            bi = q.b[t]->l[i];
+            b3_mad_row(O, av[t] + 1, bi);
+            b3_mad_row(E, av[t], bi);
+            O[11] = addc(O[11], 0);
+        }
+        uint32_t m = E[0] * FP_PINV32;
+        b3_mad_row(O, FP_P.l + 1, m);
+        b3_mad_row(E, FP_P.l, m);
+        O[11] = addc(O[11], 0);
+    }
+    even[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+    for (int i = 1; i < 11; i++) even[i] = addc_cc(even[i], odd[i + 1]);
+    even[11] = addc(even[11], 0);
+    fp_final_sub(r, even);
+}
+
 // Out-of-line multipliers take and return their operands BY VALUE: ptxas then passes them in registers, and the
 // callers' field elements never have their address taken, so they stay in registers instead of the local-memory
 // stack (by-reference noinline calls put every operand through LDL/STL: 113 M local loads in the first Miller

@@ -591,7 +591,8 @@ __global__ void __launch_bounds__(B3_TPB) k_miller_lines(const g2_jac* __restric
 // 2. slot accumulators.  grid = (chunks, B3_MILLER_SLOTS), block = 128: thread g of slot s folds the lines of pairs
 //    [g K, (g+1) K) into a dense Fp12 (sparse multiplications), the warp reduces by a shuffle tree of Fp12 products,
 //    the four warp results are multiplied CTA-cooperatively; partial[s * chunks + chunk] = product of the CTA's lines.
-__global__ void __launch_bounds__(B3_TPB) k_miller_accum(const fp2* __restrict__ lines, const uint32_t* __restrict__ qinf,
+template <int MINB>
+__global__ void __launch_bounds__(B3_TPB, MINB) k_miller_accum(const fp2* __restrict__ lines, const uint32_t* __restrict__ qinf,
                                                          const g1_pp* __restrict__ p, size_t n, unsigned K, fp12* partial) {
     __shared__ fp12 wres[B3_TPB / 32];
     __shared__ coop_ws ws;
@@ -599,7 +600,8 @@ __global__ void __launch_bounds__(B3_TPB) k_miller_accum(const fp2* __restrict__
     const size_t g = (size_t)chunk * B3_TPB + threadIdx.x;
     size_t b = g * K, e = b + K;
     if (e > n) e = n;
-    fp12 acc;
+    fp12 accA, accB;
+    fp12 *cur = &accA, *nxt = &accB;
     bool have = false;
     for (size_t j = b; j < e; j++) {
         if (qinf[j] || p[j].inf) continue;
@@ -608,10 +610,18 @@ __global__ void __launch_bounds__(B3_TPB) k_miller_accum(const fp2* __restrict__
         fp2_mul_fp(l0, l[0], p[j].ny);
         fp2_mul_fp(l3, l[1], p[j].z3);
         fp2_mul_fp(l5, l[2], p[j].xz);
-        if (have) fp12_mul_by_line(acc, l0, l3, l5);
-        else { fp12_from_line(acc, l0, l3, l5); have = true; }
+        if (have) {
+            line_ops o;
+            line_ops_make(o, l0, l3, l5);
+            fp12_mul_by_line_dot(*nxt, *cur, o);           // 12 six-term dot products, one reduction each
+            fp12* t = cur; cur = nxt; nxt = t;
+        } else {
+            fp12_from_line(*cur, l0, l3, l5);
+            have = true;
+        }
     }
-    if (!have) fp12_one(acc);
+    if (!have) fp12_one(*cur);
+    fp12& acc = *cur;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll 1
     for (int d = 16; d >= 1; d >>= 1) {

@@ -326,6 +326,51 @@ B3_FN_NOINLINE void fp12_mul_by_line(fp12& f, const fp2& l0, const fp2& l3, cons
     fp6_add(f.c0, t0, t1);
 }
 
+// Sparse-line product by dot products: r = f * (l0 + l3 w^3 + l5 w^5), r must not alias f.
+// In the w-power basis f = sum f_k w^k (w^6 = xi):
+//   r_k = l0 f_k + L3 f_{k-3 mod 6} + L5 f_{k-5 mod 6},   L3 = l3 (k >= 3) or xi l3,   L5 = l5 (k = 5) or xi l5,
+// and every Fp coordinate of r_k is ONE six-term dot product with a single Montgomery reduction (fp_dot6):
+//   re = sum X0 F0 + (-X1) F1,   im = sum X0 F1 + X1 F0     over the three (X, F) pairs.
+// 12 x 1020 multiply-accumulates and no Fp2 additions, against 14 Fp2 products plus ~40 Fp2 additions for the
+// Karatsuba form (fp12_mul_by_line).
+struct line_ops {                // operands of one line, prepared once
+    fp c0[5], c1[5], n1[5];      // X.c0, X.c1, -X.c1 for X = l0, l3, xi l3, l5, xi l5
+};
+B3_FN_NOINLINE void line_ops_make(line_ops& o, const fp2& l0, const fp2& l3, const fp2& l5) {
+    fp2 x3, x5;
+    fp2_mul_xi(x3, l3);
+    fp2_mul_xi(x5, l5);
+    const fp2* src[5] = {&l0, &l3, &x3, &l5, &x5};
+    for (int i = 0; i < 5; i++) {
+        o.c0[i] = src[i]->c0;
+        o.c1[i] = src[i]->c1;
+        fp_neg(o.n1[i], src[i]->c1);
+    }
+}
+B3_FN_NOINLINE void fp12_mul_by_line_dot(fp12& r, const fp12& f, const line_ops& o) {
+    const fp2* fc = reinterpret_cast<const fp2*>(&f);
+    fp2* rc = reinterpret_cast<fp2*>(&r);
+#pragma unroll 1
+    for (int k = 0; k < 6; k++) {
+        const int j3 = k >= 3 ? k - 3 : k + 3, j5 = k == 5 ? 0 : k + 1;
+        const int x3 = k >= 3 ? 1 : 2, x5 = k == 5 ? 3 : 4;                   // index into line_ops
+        // memory slot of w-power m in an fp12: even m -> m/2, odd m -> 3 + m/2
+        const fp2& F0 = fc[(k & 1) ? 3 + (k >> 1) : (k >> 1)];
+        const fp2& F3 = fc[(j3 & 1) ? 3 + (j3 >> 1) : (j3 >> 1)];
+        const fp2& F5 = fc[(j5 & 1) ? 3 + (j5 >> 1) : (j5 >> 1)];
+        fp2& R = rc[(k & 1) ? 3 + (k >> 1) : (k >> 1)];
+        fp_dot6_args q;
+        q.a[0] = &F0.c0; q.b[0] = &o.c0[0];  q.a[1] = &F0.c1; q.b[1] = &o.n1[0];
+        q.a[2] = &F3.c0; q.b[2] = &o.c0[x3]; q.a[3] = &F3.c1; q.b[3] = &o.n1[x3];
+        q.a[4] = &F5.c0; q.b[4] = &o.c0[x5]; q.a[5] = &F5.c1; q.b[5] = &o.n1[x5];
+        fp_dot6(R.c0, q);
+        q.a[0] = &F0.c1; q.b[0] = &o.c0[0];  q.a[1] = &F0.c0; q.b[1] = &o.c1[0];
+        q.a[2] = &F3.c1; q.b[2] = &o.c0[x3]; q.a[3] = &F3.c0; q.b[3] = &o.c1[x3];
+        q.a[4] = &F5.c1; q.b[4] = &o.c0[x5]; q.a[5] = &F5.c0; q.b[5] = &o.c1[x5];
+        fp_dot6(R.c1, q);
+    }
+}
+
 // p-power Frobenius: f_k -> conj(f_k) * GAMMA1[k]
 B3_FN fp2& fp12_coef(fp12& a, int k) {
     return (k & 1) ? ((k == 1) ? a.c1.c0 : (k == 3) ? a.c1.c1 : a.c1.c2)

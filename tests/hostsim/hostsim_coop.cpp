@@ -13,6 +13,17 @@ static void fp12_in(fp12& r, const uint8_t* b) {      // wire order w^0,w^3,w^1,
 }
 
 extern "C" {
+// out = f * (l0 + l3 w^3 + l5 w^5) through the dot-product sparse multiplication; line = 3 x 96 bytes (l0, l3, l5)
+void hc_mul_by_line_dot(const uint8_t* f576, const uint8_t* line288, uint8_t* out) {
+    fp12 f, r;
+    fp2 l0, l3, l5;
+    fp12_in(f, f576);
+    fp2_in(l0, line288); fp2_in(l3, line288 + 96); fp2_in(l5, line288 + 192);
+    line_ops o;
+    line_ops_make(o, l0, l3, l5);
+    fp12_mul_by_line_dot(r, f, o);
+    fp12_to_wire(out, r);
+}
 // out = a1*b1 + a2*b2 mod p through the dual-product Montgomery routine (fp.cuh: fp_mul2)
 void hc_fp_mul2(const uint8_t* a1, const uint8_t* b1, const uint8_t* a2, const uint8_t* b2, uint8_t* out) {
     fp x1, y1, x2, y2, r, t;

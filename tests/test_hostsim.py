@@ -311,3 +311,16 @@ def test_fp_mul2(hc):
         out = ctypes.create_string_buffer(48)
         hc.hc_fp_mul2(b48(a1), b48(b1), b48(a2), b48(b2), out)
         assert int.from_bytes(out.raw, "big") == (a1 * b1 + a2 * b2) % p
+
+
+def test_sparse_line_product_by_dot(hc):
+    for trial in range(4):
+        f = rf12()
+        l0, l3, l5 = rfp2(), rfp2(), rfp2()
+        if trial == 3:
+            l0, l3, l5 = (p - 1, p - 1), (0, p - 1), (p - 1, 0)
+        # the line as a dense Fp12 in the reference's 2-2-3 layout: a + b w + c w^2, a = (w^0, w^3), b = (w^1, w^4), c = (w^2, w^5)
+        line = ((l0, l3), ((0, 0), (0, 0)), ((0, 0), l5))
+        out = ctypes.create_string_buffer(576)
+        hc.hc_mul_by_line_dot(O.f12_to_bytes(f), fp2b(l0) + fp2b(l3) + fp2b(l5), out)
+        assert out.raw == O.f12_to_bytes(O.f12_mul(f, line))
