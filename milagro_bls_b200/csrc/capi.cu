@@ -225,9 +225,7 @@ static int miller_reserve(b3_ctx* ctx, size_t n_pairs) {
 }
 // steps 2 and 3 (context stream): per-slot accumulation over all pairs, one cooperative closing chain -> *res
 static int miller_finish(b3_ctx* ctx, const g1_pp* p, size_t n_pairs, fp12** res) {
-    const char* ek = getenv("B3_ACC_K");
-    size_t kk = ek ? (size_t)atoi(ek) : 16;
-    size_t chunks = (n_pairs + 64 * kk) / (128 * kk);              // ~16 pairs per accumulating thread
+    size_t chunks = (n_pairs + 1024) / 2048;              // ~16 pairs per accumulating thread (measured optimum: 8 and 32 are 25 % slower)
     if (chunks < 1) chunks = 1;
     if (chunks > 64) chunks = 64;
     unsigned K = (unsigned)((n_pairs + chunks * B3_TPB - 1) / (chunks * B3_TPB));
@@ -242,11 +240,7 @@ static int miller_finish(b3_ctx* ctx, const g1_pp* p, size_t n_pairs, fp12** res
     }
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     int sp = span_begin(ctx, ST_MILLER, ctx->stream);
-    const char* elb = getenv("B3_ACC_LB");
-    int lb = elb ? atoi(elb) : 1;
-    if (lb == 3) LAUNCH(k_miller_accum<3>, dim3((unsigned)chunks, B3_MILLER_SLOTS), B3_TPB, (const fp2*)ctx->lines.p, (const uint32_t*)ctx->qinf.p, p, n_pairs, K, partial);
-    else if (lb == 4) LAUNCH(k_miller_accum<4>, dim3((unsigned)chunks, B3_MILLER_SLOTS), B3_TPB, (const fp2*)ctx->lines.p, (const uint32_t*)ctx->qinf.p, p, n_pairs, K, partial);
-    else LAUNCH(k_miller_accum<1>, dim3((unsigned)chunks, B3_MILLER_SLOTS), B3_TPB, (const fp2*)ctx->lines.p, (const uint32_t*)ctx->qinf.p, p, n_pairs, K, partial);
+    LAUNCH(k_miller_accum, dim3((unsigned)chunks, B3_MILLER_SLOTS), B3_TPB, (const fp2*)ctx->lines.p, (const uint32_t*)ctx->qinf.p, p, n_pairs, K, partial);
     span_end(ctx, sp, ctx->stream);
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     sp = span_begin(ctx, ST_FP12_PRODUCT, ctx->stream);

@@ -591,8 +591,7 @@ __global__ void __launch_bounds__(B3_TPB) k_miller_lines(const g2_jac* __restric
 // 2. slot accumulators.  grid = (chunks, B3_MILLER_SLOTS), block = 128: thread g of slot s folds the lines of pairs
 //    [g K, (g+1) K) into a dense Fp12 (sparse multiplications), the warp reduces by a shuffle tree of Fp12 products,
 //    the four warp results are multiplied CTA-cooperatively; partial[s * chunks + chunk] = product of the CTA's lines.
-template <int MINB>
-__global__ void __launch_bounds__(B3_TPB, MINB) k_miller_accum(const fp2* __restrict__ lines, const uint32_t* __restrict__ qinf,
+__global__ void __launch_bounds__(B3_TPB) k_miller_accum(const fp2* __restrict__ lines, const uint32_t* __restrict__ qinf,
                                                          const g1_pp* __restrict__ p, size_t n, unsigned K, fp12* partial) {
     __shared__ fp12 wres[B3_TPB / 32];
     __shared__ coop_ws ws;
