@@ -436,6 +436,38 @@ def test_verify_multiple_large_batch_vs_c_oracle(eng):
     assert not ok and not ok_c and fb == -1 and gt == gt_c and gt != O.f12_to_bytes(O.F12_ONE)
 
 
+def test_verify_multiple_large_batch_edge_sets(eng):
+    """Bucket-method / multi-chunk path (n >= 512) with the edge cases of SURVEY.md appendix C inside the batch:
+    an (infinity signature, infinity key) set, a pre-aggregated-key call (pk_off = None), duplicate scalars, and --
+    in a second call -- a non-subgroup signature whose index must come back as first_bad."""
+    from oracle import c_oracle
+    rnd = random.Random(12)
+    n = 530
+    sks = [rnd.randrange(1, O.r) for _ in range(n)]
+    pk = eng.g1_mul_gen(sks).copy()
+    msgs = [bytes(rnd.getrandbits(8) for _ in range(32)) for _ in range(n)]
+    H = eng.hash_to_g2(msgs)
+    sig = eng.g2_mul(H.reshape(-1), sks).copy()
+    inf1 = np.frombuffer(g1w(None), dtype=np.uint8)
+    inf2 = np.frombuffer(g2w(None), dtype=np.uint8)
+    pk[17] = inf1; sig[17] = inf2                                # e(H, inf) = 1 and nothing added to S: still valid
+    scalars = np.array([rnd.randrange(1, 1 << 63) for _ in range(n)], dtype=np.uint64)
+    scalars[40] = scalars[41] = scalars[42] = 0x0101010101010101     # same digit in every window
+    moff = list(range(0, 32 * n + 1, 32))
+    ok, fb, gt = eng.verify_multiple(sig.reshape(-1), pk.reshape(-1), None, b"".join(msgs), moff, scalars, want_gt=True)
+    ok_c, gt_c = c_oracle.verify_multiple(sig.reshape(-1), pk.reshape(-1), None, b"".join(msgs), moff, scalars)
+    assert ok and ok_c and fb == -1 and gt == gt_c == O.f12_to_bytes(O.F12_ONE)
+    # swap two signatures: reject, GT equals the C oracle's
+    sw = sig.copy(); sw[[5, 6]] = sw[[6, 5]]
+    ok, fb, gt = eng.verify_multiple(sw.reshape(-1), pk.reshape(-1), None, b"".join(msgs), moff, scalars, want_gt=True)
+    ok_c, gt_c = c_oracle.verify_multiple(sw.reshape(-1), pk.reshape(-1), None, b"".join(msgs), moff, scalars)
+    assert not ok and not ok_c and fb == -1 and gt == gt_c
+    # non-subgroup signature deep inside the batch
+    bad = sig.copy(); bad[377] = np.frombuffer(g2w(O.map_to_curve_g2((5, 7))), dtype=np.uint8)
+    ok, fb = eng.verify_multiple(bad.reshape(-1), pk.reshape(-1), None, b"".join(msgs), moff, scalars)
+    assert not ok and fb == 377
+
+
 def test_imad_probe_runs(eng):
     assert eng.imad_peak(False) > 1e12
     assert eng.imad_peak(True) > 1e11
