@@ -11,6 +11,10 @@
 #define B3_ERR_INVALID_G2_SIZE_D (-7)
 
 #define B3_TPB 128
+#ifndef B3_MIN_CTAS
+#define B3_MIN_CTAS 2
+#endif
+#define B3_LBH __launch_bounds__(B3_TPB, B3_MIN_CTAS)
 
 // G1 member of a pairing in the form the line scaling wants: for P = (X : Y : Z) Jacobian (x = X/Z^2, y = Y/Z^3)
 // the line  l0 = u0 (-y), l3, l5 = u5 x  times Z^3 is  u0 (-Y), l3 Z^3, u5 (X Z)  -- no inversion.
@@ -53,7 +57,7 @@ __global__ void __launch_bounds__(B3_TPB) k_g2_parse(const uint8_t* __restrict__
 }
 // subgroup_check_g2 on parsed signatures: ok[i] = parsed fine && in G2 (infinity passes).
 // LANE PAIRS (fp2h.cuh): threads (2i, 2i+1) work on signature i.
-__global__ void __launch_bounds__(B3_TPB) k_g2_subgroup(const g2_aff* pts, const int32_t* status, size_t n, int32_t* ok) {
+__global__ void B3_LBH k_g2_subgroup(const g2_aff* pts, const int32_t* status, size_t n, int32_t* ok) {
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     if (i >= n) return;
     int good = 0;
@@ -364,7 +368,7 @@ __global__ void __launch_bounds__(B3_TPB) k_g2_mul_u256(const uint8_t* __restric
 #define B3_MSM_BUCKETS 255
 #define B3_MSM_SEGS 4
 #define B3_MSM_LIST 24
-__global__ void __launch_bounds__(B3_TPB) k_msm_bucket(const g2_aff* __restrict__ sigs, const uint64_t* __restrict__ k, size_t n, g2_jac* parts) {
+__global__ void B3_LBH k_msm_bucket(const g2_aff* __restrict__ sigs, const uint64_t* __restrict__ k, size_t n, g2_jac* parts) {
     const size_t id = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     if (id >= (size_t)B3_MSM_WINDOWS * B3_MSM_BUCKETS * B3_MSM_SEGS) return;
     const unsigned seg = (unsigned)(id % B3_MSM_SEGS);
@@ -395,7 +399,7 @@ __global__ void __launch_bounds__(B3_TPB) k_msm_bucket(const g2_aff* __restrict_
     g2h_store(parts[id], acc);
 }
 // out[w * 256 + (b - 1)] = [b] * sum_seg parts;  out[w * 256 + 255] = infinity (padding for the window tree)
-__global__ void __launch_bounds__(B3_TPB) k_msm_scale(const g2_jac* parts, g2_jac* out) {
+__global__ void B3_LBH k_msm_scale(const g2_jac* parts, g2_jac* out) {
     const size_t id = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     if (id >= (size_t)B3_MSM_WINDOWS * 256) return;
     const unsigned w = (unsigned)(id >> 8), bi = (unsigned)(id & 255);
@@ -488,7 +492,7 @@ __global__ void __launch_bounds__(B3_TPB) k_g2_aff_to_wire(const g2_aff* in, siz
 // Two threads per message.  Phase 1: each lane maps ONE of the two field elements to the curve (SSWU + 3-isogeny,
 // single-thread Fp2 arithmetic: the square roots are chains of Fp operations).  Phase 2: the two points are
 // redistributed into lane-pair form and the pair adds them and clears the cofactor together.
-__global__ void __launch_bounds__(B3_TPB) k_hash_to_g2(const uint8_t* __restrict__ msgs, const uint32_t* __restrict__ off, size_t n,
+__global__ void B3_LBH k_hash_to_g2(const uint8_t* __restrict__ msgs, const uint32_t* __restrict__ off, size_t n,
                                                        const uint8_t* __restrict__ dst, uint32_t dst_len, g2_jac* out) {
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     if (i >= n) return;
@@ -558,7 +562,7 @@ __global__ void __launch_bounds__(B3_TPB) k_g2_aff_to_jac(const g2_aff* in, size
 // 1. point chain of every pair -> unscaled lines, lines[(slot * n + pair) * 3 + {0,1,2}] = (u0, l3, u5)
 //    LANE PAIRS: threads (2i, 2i+1) run the chain of pair i, each storing its half of every coefficient.
 //    Pairs [first, first + count) of the n pairs of the product (different ranges may run on different streams).
-__global__ void __launch_bounds__(B3_TPB) k_miller_lines(const g2_jac* __restrict__ q, size_t n, size_t first, size_t count,
+__global__ void B3_LBH k_miller_lines(const g2_jac* __restrict__ q, size_t n, size_t first, size_t count,
                                                          fp2* __restrict__ lines, uint32_t* __restrict__ qinf) {
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     if (i >= count) return;
@@ -591,7 +595,7 @@ __global__ void __launch_bounds__(B3_TPB) k_miller_lines(const g2_jac* __restric
 // 2. slot accumulators.  grid = (chunks, B3_MILLER_SLOTS), block = 128: thread g of slot s folds the lines of pairs
 //    [g K, (g+1) K) into a dense Fp12 (sparse multiplications), the warp reduces by a shuffle tree of Fp12 products,
 //    the four warp results are multiplied CTA-cooperatively; partial[s * chunks + chunk] = product of the CTA's lines.
-__global__ void __launch_bounds__(B3_TPB) k_miller_accum(const fp2* __restrict__ lines, const uint32_t* __restrict__ qinf,
+__global__ void B3_LBH k_miller_accum(const fp2* __restrict__ lines, const uint32_t* __restrict__ qinf,
                                                          const g1_pp* __restrict__ p, size_t n, unsigned K, fp12* partial) {
     __shared__ fp12 wres[B3_TPB / 32];
     __shared__ coop_ws ws;
