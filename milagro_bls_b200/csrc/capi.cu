@@ -225,10 +225,13 @@ static int miller_reserve(b3_ctx* ctx, size_t n_pairs) {
 }
 // steps 2 and 3 (context stream): per-slot accumulation over all pairs, one cooperative closing chain -> *res
 static int miller_finish(b3_ctx* ctx, const g1_pp* p, size_t n_pairs, fp12** res) {
-    size_t chunks = (n_pairs + 1024) / 2048;              // ~16 pairs per accumulating thread (measured optimum: 8 and 32 are 25 % slower)
+    // K pairs per accumulating six-lane group, 20 groups per CTA (k_miller_accum)
+    static const unsigned kTargetK = getenv("B3_ACC_K") ? (unsigned)atoi(getenv("B3_ACC_K")) : 32u;
+    size_t chunks = (n_pairs + (size_t)B3_ACC_GROUPS * kTargetK - 1) / ((size_t)B3_ACC_GROUPS * kTargetK);
     if (chunks < 1) chunks = 1;
     if (chunks > 64) chunks = 64;
-    unsigned K = (unsigned)((n_pairs + chunks * B3_TPB - 1) / (chunks * B3_TPB));
+    unsigned K = (unsigned)((n_pairs + chunks * B3_ACC_GROUPS - 1) / (chunks * B3_ACC_GROUPS));
+    if (K < 1) K = 1;
     CKR(ensure(ctx, ctx->f12a, sizeof(fp12) * (B3_MILLER_SLOTS * (chunks + 1) + 2)));
     fp12* partial = (fp12*)ctx->f12a.p;
     fp12* slotvals = partial + B3_MILLER_SLOTS * chunks;

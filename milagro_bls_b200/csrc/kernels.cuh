@@ -592,52 +592,106 @@ __global__ void B3_LBH k_miller_lines(const g2_jac* __restrict__ q, size_t n, si
         }
     }
 }
-// 2. slot accumulators.  grid = (chunks, B3_MILLER_SLOTS), block = 128: thread g of slot s folds the lines of pairs
-//    [g K, (g+1) K) into a dense Fp12 (sparse multiplications), the warp reduces by a shuffle tree of Fp12 products,
-//    the four warp results are multiplied CTA-cooperatively; partial[s * chunks + chunk] = product of the CTA's lines.
-__global__ void B3_LBH k_miller_accum(const fp2* __restrict__ lines, const uint32_t* __restrict__ qinf,
-                                                         const g1_pp* __restrict__ p, size_t n, unsigned K, fp12* partial) {
-    __shared__ fp12 wres[B3_TPB / 32];
+// 2. slot accumulators, GROUP-COOPERATIVE: six lanes own one dense Fp12 accumulator, lane k holding the Fp2 coefficient of
+//    w^k in registers (five groups per warp, lanes 30/31 idle; B3_ACC_GROUPS = 20 groups per CTA).  grid = (chunks,
+//    B3_MILLER_SLOTS): group g of chunk c folds the lines of pairs [(c * 20 + g) K, +K) of its slot:
+//      a. lane t scales one Fp coordinate of the line by its factor of P (times Z_P^3, an Fp factor) -> shared memory
+//      b. the group derives -X.c1 and the xi multiples (line_ops layout) in shared memory
+//      c. lane k gathers the coefficients of w^(k+3) and w^(k+1) by warp shuffles and computes
+//           r_k = l0 f_k + L3 f_{k-3} + L5 f_{k-5}      (tower.cuh, fp12_mul_by_line_dot)
+//         as two six-term dot products with one reduction each (fp_dot6_rs).
+//    The accumulator never leaves registers (the one-thread-per-accumulator version kept 2 x 576 B per thread in local
+//    memory and thrashed L1: profiles/r1n_accum_full.txt).  The 20 group results are multiplied CTA-cooperatively;
+//    partial[s * chunks + chunk] = product of the CTA's lines.
+#define B3_ACC_GROUPS 20
+// line operands of one group in shared memory: v[0..4] = X.c0, v[5..9] = X.c1, v[10..14] = -X.c1 for X = l0, l3, xi l3, l5, xi l5
+// (the line_ops layout of tower.cuh), v[15] = 0, v[16], v[17] = write-only sinks for lanes with nothing to derive
+struct acc_ops {
+    fp v[18];
+};
+__global__ void __launch_bounds__(B3_TPB, 3) k_miller_accum(const fp2* __restrict__ lines, const uint32_t* __restrict__ qinf,
+                                                            const g1_pp* __restrict__ p, size_t n, unsigned K, fp12* partial) {
+    __shared__ acc_ops ops[B3_ACC_GROUPS];
+    __shared__ fp12 tree[B3_ACC_GROUPS];
     __shared__ coop_ws ws;
     const unsigned slot = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
-    const size_t g = (size_t)chunk * B3_TPB + threadIdx.x;
-    size_t b = g * K, e = b + K;
-    if (e > n) e = n;
-    fp12 accA, accB;
-    fp12 *cur = &accA, *nxt = &accB;
-    bool have = false;
-    for (size_t j = b; j < e; j++) {
-        if (qinf[j] || p[j].inf) continue;
-        const fp2* l = lines + ((size_t)slot * n + j) * 3;
-        fp2 l0, l3, l5;                                    // the line times Z_P^3 (an Fp factor)
-        fp2_mul_fp(l0, l[0], p[j].ny);
-        fp2_mul_fp(l3, l[1], p[j].z3);
-        fp2_mul_fp(l5, l[2], p[j].xz);
-        if (have) {
-            line_ops o;
-            line_ops_make(o, l0, l3, l5);
-            fp12_mul_by_line_dot(*nxt, *cur, o);           // 12 six-term dot products, one reduction each
-            fp12* t = cur; cur = nxt; nxt = t;
-        } else {
-            fp12_from_line(*cur, l0, l3, l5);
-            have = true;
-        }
-    }
-    if (!have) fp12_one(*cur);
-    fp12& acc = *cur;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll 1
-    for (int d = 16; d >= 1; d >>= 1) {
-        fp12 o;
-        shfl_down_struct(o, acc, d, 32);
-        if (lane < d) fp12_mul(acc, acc, o);
+    const int gl = lane / 6, k = lane - 6 * gl;
+    const bool live = gl < 5;
+    const int g = warp * 5 + (live ? gl : 0);
+    const int src3 = (6 * gl + (k + 3) % 6) & 31, src5 = (6 * gl + (k + 1) % 6) & 31;
+    fp* const o = ops[g].v;
+    // where lane k's scaled coordinate goes: (l0.c0, l0.c1, l3.c0, l3.c1, l5.c0, l5.c1) -> X slots 0, 1, 3
+    fp* const mine = o + ((k & 1) ? 5 : 0) + ((k >> 1) == 2 ? 3 : (k >> 1));
+    // branch-free derivation, lane k:  o[d1] = o[x1] - o[y1];  t = o[u2] + o[v2] -> o[d2];  o[d3] = 0 - t
+    //   k = 0, 1, 4: -X.c1 of l0, l3, l5     k = 2: xi l3 = (c0 - c1, c0 + c1) and -(c0 + c1)     k = 3: the same for l5
+    const int Z = 15, S0 = 16, S1 = 17;
+    const int x1 = k == 2 ? 1 : k == 3 ? 3 : Z;
+    const int y1 = k == 0 ? 5 : k == 1 ? 6 : k == 2 ? 6 : k == 3 ? 8 : k == 4 ? 8 : Z;
+    const int d1 = k == 0 ? 10 : k == 1 ? 11 : k == 2 ? 2 : k == 3 ? 4 : k == 4 ? 13 : S0;
+    const int u2 = k == 2 ? 1 : k == 3 ? 3 : Z, v2 = k == 2 ? 6 : k == 3 ? 8 : Z;
+    const int d2 = k == 2 ? 7 : k == 3 ? 9 : S0, d3 = k == 2 ? 12 : k == 3 ? 14 : S1;
+    if (live && k == 0) o[Z] = FP_NIL;
+    const int x3 = k >= 3 ? 1 : 2, x5 = k == 5 ? 3 : 4;
+    const size_t first = ((size_t)chunk * B3_ACC_GROUPS + g) * K;
+    fp a[6];                                               // a[0], a[1]: this lane's coefficient (c0, c1); a[2..5]: gathered
+    a[0] = FP_NIL; a[1] = FP_NIL;
+    bool have = false;
+    for (unsigned it = 0; it < K; it++) {
+        const size_t j = first + it;
+        bool valid = live && j < n;
+        if (valid) valid = !(qinf[j] || p[j].inf);
+        if (valid) {
+            fp v = reinterpret_cast<const fp*>(lines + ((size_t)slot * n + j) * 3)[k];
+            const fp f = (k >> 1) == 0 ? p[j].ny : (k >> 1) == 1 ? p[j].z3 : p[j].xz;
+            *mine = fp_mul_v(v, f);
+        }
+        __syncwarp();
+        if (valid) {
+            fp t;
+            fp_sub(t, o[x1], o[y1]);
+            o[d1] = t;
+            fp_add(t, o[u2], o[v2]);
+            if (k == 2 || k == 3) o[d2] = t;
+            fp_sub(t, o[Z], t);
+            o[d3] = t;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int w = 0; w < 12; w++) {
+            a[2].l[w] = __shfl_sync(0xffffffffu, a[0].l[w], src3);
+            a[3].l[w] = __shfl_sync(0xffffffffu, a[1].l[w], src3);
+            a[4].l[w] = __shfl_sync(0xffffffffu, a[0].l[w], src5);
+            a[5].l[w] = __shfl_sync(0xffffffffu, a[1].l[w], src5);
+        }
+        if (valid) {
+            if (have) {
+                fp r0, r1;
+                fp_dot6_rs(r0, a, o, o + 10, o + x3, o + 10 + x3, o + x5, o + 10 + x5);
+                fp_dot6_rs(r1, a, o + 5, o, o + 5 + x3, o + x3, o + 5 + x5, o + x5);
+                a[0] = r0; a[1] = r1;
+            } else {                                           // first line: f = l0 + l3 w^3 + l5 w^5
+                const int sl = k == 0 ? 0 : k == 3 ? 1 : 3;
+                const bool nz = k == 0 || k == 3 || k == 5;
+                fp_select(a[0], nz, o[sl], FP_NIL);
+                fp_select(a[1], nz, o[5 + sl], FP_NIL);
+                have = true;
+            }
+        }
+        __syncwarp();
     }
-    if (lane == 0) wres[warp] = acc;
+    if (live) {
+        if (!have) { fp_select(a[0], k == 0, FP_ONE, FP_NIL); a[1] = FP_NIL; }
+        fp2& d = coop_coef(tree[g], k);
+        d.c0 = a[0]; d.c1 = a[1];
+    }
     __syncthreads();
-    coop_fp12_mul(wres[0], wres[0], wres[1], ws);
-    coop_fp12_mul(wres[2], wres[2], wres[3], ws);
-    coop_fp12_mul(wres[0], wres[0], wres[2], ws);
-    coop_copy_p(partial[(size_t)slot * chunks + chunk], wres[0], (int)threadIdx.x);
+    // groups that had pairs in range: at least one, at most all
+    size_t left = n > (size_t)chunk * B3_ACC_GROUPS * K ? n - (size_t)chunk * B3_ACC_GROUPS * K : 0;
+    unsigned used = (unsigned)((left + K - 1) / K);
+    if (used > B3_ACC_GROUPS) used = B3_ACC_GROUPS;
+    for (unsigned t = 1; t < used; t++) coop_fp12_mul(tree[0], tree[0], tree[t], ws);
+    coop_copy_p(partial[(size_t)slot * chunks + chunk], tree[0], (int)threadIdx.x);
 }
 // 2b. one CTA per slot: slot value = product of that slot's per-chunk partials (only launched when chunks > 1)
 __global__ void __launch_bounds__(B3_COOP_THREADS) k_miller_slots(const fp12* partial, unsigned chunks, fp12* slotvals) {
