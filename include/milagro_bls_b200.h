@@ -109,6 +109,23 @@ int b3_verify_multiple(b3_ctx*, const uint8_t* sigs192, const uint8_t* pks96, co
                        const uint8_t* msgs, const uint32_t* msg_off, const uint64_t* scalars, size_t n,
                        int* accept, int64_t* first_bad, uint8_t* gt576);
 
+/* ---- batched verification of n INDEPENDENT items with one accept bit each (locating the bad set
+ *      after a batch reject, or bulk verification of unrelated signatures).  Item i is, by `mode`,
+ *        B3_ITEM_VERIFY          Signature::verify(sig_i, msg_i, pk_i)                           (M/src/signature.rs:27-40)
+ *        B3_ITEM_FAST_AGGREGATE  fast_aggregate_verify(sig_i, msg_i, pks96[pk_off[i] .. pk_off[i+1]))  (M/src/aggregates.rs:177-215)
+ *        B3_ITEM_PRE_AGGREGATED  fast_aggregate_verify_pre_aggregated(sig_i, msg_i, apk_i)       (M/src/aggregates.rs:223-253)
+ *      (pk_off is read only in mode B3_ITEM_FAST_AGGREGATE; otherwise pks96 holds one key per item).
+ *      accept[i] = the reference's bool; status[i] = B3_OK or the AmclError code of a malformed input of item i
+ *      (B3_ERR_AGGREGATE_EMPTY_POINTS for an empty key list; accept[i] = 0 in every such case);
+ *      gt576 (nullable, n x 576 B) = each item's FP12 after fexp, all-zero for items rejected before the pairing.
+ *      One final exponentiation PER ITEM, one CTA per item. ---- */
+#define B3_ITEM_VERIFY 0
+#define B3_ITEM_FAST_AGGREGATE 1
+#define B3_ITEM_PRE_AGGREGATED 2
+int b3_verify_batch(b3_ctx*, int mode, const uint8_t* sigs192, const uint8_t* pks96, const uint32_t* pk_off,
+                    const uint8_t* msgs, const uint32_t* msg_off, size_t n, int32_t* accept, int32_t* status,
+                    uint8_t* gt576);
+
 /* ---- device-resident variants (inputs already in HBM; used for multi-GPU sharding and resident benchmarks).
  *      partial_dev receives this rank's Miller-loop product (B3_PARTIAL_BYTES of device memory, internal
  *      Montgomery layout -- only meaningful to b3_combine_partials_dev of the same library build).
@@ -120,6 +137,9 @@ int b3_verify_multiple_partial_dev(b3_ctx*, const uint8_t* sigs192_dev, const ui
 /* product of n_partials partials (gathered from all ranks) -> one final exponentiation -> accept, first_bad, gt */
 int b3_combine_partials_dev(b3_ctx*, const uint8_t* partials_dev, size_t n_partials, int* accept, int64_t* first_bad,
                             uint8_t* gt576);
+int b3_verify_batch_dev(b3_ctx*, int mode, const uint8_t* sigs192_dev, const uint8_t* pks96_dev,
+                        const uint32_t* pk_off_dev, const uint8_t* msgs_dev, const uint32_t* msg_off_dev, size_t n,
+                        int32_t* accept_dev, int32_t* status_dev, uint8_t* gt576_dev);
 int b3_hash_to_g2_dev(b3_ctx*, const uint8_t* msgs_dev, const uint32_t* off_dev, size_t n, uint8_t* out192_dev);
 int b3_g1_aggregate_dev(b3_ctx*, const uint8_t* pks96_dev, const uint32_t* off_dev, size_t n_sets, uint8_t* out96_dev,
                         int32_t* status_dev);

@@ -16,6 +16,7 @@ ERR_NAMES = {
     -5: "InvalidPoint", -6: "InvalidG1Size", -7: "InvalidG2Size", -8: "InvalidYFlag", -100: "CudaError", -101: "BadArgument",
 }
 PARTIAL_BYTES = 592
+ITEM_VERIFY, ITEM_FAST_AGGREGATE, ITEM_PRE_AGGREGATED = 0, 1, 2
 
 
 class B3LibraryMissing(RuntimeError):
@@ -61,6 +62,8 @@ def lib():
         "b3_fast_aggregate_verify_pre_aggregated": ([vp, u8p, u8p, u8p, sz, ip, u8p], ctypes.c_int),
         "b3_aggregate_verify": ([vp, u8p, u8p, u8p, vp, sz, ip, u8p], ctypes.c_int),
         "b3_verify_multiple": ([vp, u8p, u8p, vp, u8p, vp, vp, sz, ip, i64p, u8p], ctypes.c_int),
+        "b3_verify_batch": ([vp, ctypes.c_int, u8p, u8p, vp, u8p, vp, sz, i32p, i32p, u8p], ctypes.c_int),
+        "b3_verify_batch_dev": ([vp, ctypes.c_int, vp, vp, vp, vp, vp, sz, vp, vp, vp], ctypes.c_int),
         "b3_verify_multiple_partial_dev": ([vp, vp, vp, vp, vp, vp, vp, sz, ctypes.c_int64, vp], ctypes.c_int),
         "b3_combine_partials_dev": ([vp, vp, sz, ip, i64p, u8p], ctypes.c_int),
         "b3_hash_to_g2_dev": ([vp, vp, vp, sz, vp], ctypes.c_int),
@@ -84,6 +87,7 @@ EXPORTED_SYMBOLS = [
     "b3_g1_decompress", "b3_g2_decompress", "b3_g1_compress", "b3_g2_compress", "b3_g1_validate", "b3_g2_subgroup_check",
     "b3_g1_aggregate", "b3_g2_aggregate", "b3_hash_to_g2", "b3_verify", "b3_fast_aggregate_verify",
     "b3_fast_aggregate_verify_pre_aggregated", "b3_aggregate_verify", "b3_verify_multiple",
+    "b3_verify_batch", "b3_verify_batch_dev",
     "b3_verify_multiple_partial_dev", "b3_combine_partials_dev", "b3_hash_to_g2_dev", "b3_g1_aggregate_dev",
     "b3_g1_mul_gen", "b3_g2_mul", "b3_imad_peak",
 ]

@@ -244,6 +244,32 @@ class Engine:
                                            ctypes.byref(ok), ctypes.byref(fb), gt.ctypes.data))
         return (bool(ok.value), int(fb.value), gt.tobytes()) if want_gt else (bool(ok.value), int(fb.value))
 
+    def verify_batch(self, mode, sigs192, pks96, pk_offsets, msgs, want_gt=False):
+        """n independent items, one accept bit each (b3_verify_batch).  mode: _lib.ITEM_VERIFY (one key per item),
+        ITEM_FAST_AGGREGATE (keys of item i = pks96[pk_offsets[i]:pk_offsets[i+1]]), ITEM_PRE_AGGREGATED.
+        msgs: list of byte strings.  Returns (accept[n] bool array, status[n] int32 array[, gt (n, 576) uint8])."""
+        n = len(msgs)
+        accept = np.zeros(max(n, 1), dtype=np.int32)
+        status = np.zeros(max(n, 1), dtype=np.int32)
+        gt = np.zeros((max(n, 1), 576), dtype=np.uint8) if want_gt else None
+        off = _offsets(msgs)
+        ps, k1 = _buf(sigs192)
+        pp, k2 = _buf(pks96)
+        pm, k3 = _buf(b"".join(msgs))
+        po = None
+        if pk_offsets is not None:
+            koff = np.ascontiguousarray(pk_offsets, dtype=np.uint32)
+            po = koff.ctypes.data
+        self._ck(self.L.b3_verify_batch(self.handle, mode, ps, pp, po, pm, off.ctypes.data, n,
+                                        accept.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                        status.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                        gt.ctypes.data if want_gt else None))
+        res = (accept[:n].astype(bool), status[:n])
+        return res + (gt[:n],) if want_gt else res
+
+    def verify_batch_dev(self, mode, d_sigs, d_pks, d_pk_off, d_msgs, d_msg_off, n, d_accept, d_status, d_gt=None):
+        self._ck(self.L.b3_verify_batch_dev(self.handle, mode, d_sigs, d_pks, d_pk_off, d_msgs, d_msg_off, n, d_accept, d_status, d_gt))
+
     # device-pointer forms (torch tensors / raw addresses), used by bench.py and the multi-GPU path
     def verify_multiple_partial_dev(self, d_sigs, d_pks, d_pk_off, d_msgs, d_msg_off, d_scalars, n, index_base, d_partial):
         self._ck(self.L.b3_verify_multiple_partial_dev(self.handle, d_sigs, d_pks, d_pk_off, d_msgs, d_msg_off, d_scalars, n,

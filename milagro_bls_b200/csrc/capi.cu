@@ -609,6 +609,127 @@ extern "C" int b3_aggregate_verify(b3_ctx* ctx, const uint8_t sig192[192], const
     return B3_OK;
 }
 
+// ---- batched per-item verification: n independent items, one accept bit each ------------------------
+static int verify_batch_core(b3_ctx* ctx, int mode, const uint8_t* d_sigs, const uint8_t* d_pks, const uint32_t* d_pk_off, size_t total_keys,
+                             const uint8_t* d_msgs, const uint32_t* d_msg_off, size_t n, int32_t* d_accept, int32_t* d_status, uint8_t* d_gt) {
+    CKR(ensure(ctx, ctx->g2a_sig, sizeof(g2_aff) * n));
+    CKR(ensure(ctx, ctx->status, 4 * (2 * n + 8)));
+    CKR(ensure(ctx, ctx->ok, 4 * (n + 8)));
+    CKR(ensure(ctx, ctx->g1j, sizeof(g1_jac) * n));
+    CKR(ensure(ctx, ctx->g1pp, sizeof(g1_pp) * n));
+    CKR(ensure(ctx, ctx->g2q, sizeof(g2_jac) * 2 * n));
+    CKR(miller_reserve(ctx, 2 * n));
+    int32_t* d_st_sig = (int32_t*)ctx->status.p;
+    int32_t* d_st_key = d_st_sig + n + 4;
+    g2_jac* q = (g2_jac*)ctx->g2q.p;              // q[0 .. n) = signatures, q[n .. 2n) = H(msg)
+    g1_pp* keys = (g1_pp*)ctx->g1pp.p;
+    cudaStream_t sm = ctx->stream;
+    cudaStream_t s0 = ctx->serial ? sm : ctx->aux[0], s1 = ctx->serial ? sm : ctx->aux[1], s2 = ctx->serial ? sm : ctx->aux[2];
+    int sp;
+    if (!ctx->serial) {
+        CK(cudaEventRecord(ctx->ev_fork, sm));
+        CK(cudaStreamWaitEvent(s1, ctx->ev_fork, 0));
+        CK(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
+    }
+    // H_i = hash_to_curve_g2(msg_i) and its point chain: the longest dependent chain, issued first
+    sp = span_begin(ctx, ST_HASH_TO_G2, s2);
+    CKR(hash_to_g2_jac_dev(ctx, s2, d_msgs, d_msg_off, n, q + n));
+    span_end(ctx, sp, s2);
+    CKR(miller_lines(ctx, s2, q, 2 * n, n, n));
+    // signatures: parse + on-curve, then the subgroup checks (aux0) beside their point chains (main)
+    sp = span_begin(ctx, ST_COPY, sm);
+    LAUNCH_ON(sm, k_g2_parse, nblk(n), B3_TPB, d_sigs, n, (g2_aff*)ctx->g2a_sig.p, d_st_sig, 1);
+    LAUNCH_ON(sm, k_g2_aff_to_jac, nblk(n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, n, q);
+    span_end(ctx, sp, sm);
+    if (!ctx->serial) {
+        CK(cudaEventRecord(ctx->ev_fork2, sm));
+        CK(cudaStreamWaitEvent(s0, ctx->ev_fork2, 0));
+    }
+    sp = span_begin(ctx, ST_SIG_CHECK, s0);
+    LAUNCH_ON(s0, k_g2_subgroup, nblk(2 * n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, (const int32_t*)d_st_sig, n, (int32_t*)ctx->ok.p);
+    span_end(ctx, sp, s0);
+    CKR(miller_lines(ctx, sm, q, 2 * n, 0, n));
+    // keys: aggregate (fast_aggregate_verify) or parse (verify / pre-aggregated) -> pairing form
+    sp = span_begin(ctx, ST_AGGREGATE, s1);
+    if (mode == B3_ITEM_FAST_AGGREGATE) {
+        size_t avg = total_keys / n;
+        if (n >= 16384 || avg <= 8) LAUNCH_ON(s1, k_g1_aggregate<4>, nblk(n * 4), B3_TPB, d_pks, d_pk_off, n, (g1_jac*)ctx->g1j.p, d_st_key);
+        else if (n >= 2048 || avg <= 32) LAUNCH_ON(s1, k_g1_aggregate<8>, nblk(n * 8), B3_TPB, d_pks, d_pk_off, n, (g1_jac*)ctx->g1j.p, d_st_key);
+        else LAUNCH_ON(s1, k_g1_aggregate<32>, nblk(n * 32), B3_TPB, d_pks, d_pk_off, n, (g1_jac*)ctx->g1j.p, d_st_key);
+    } else {
+        LAUNCH_ON(s1, k_g1_parse, nblk(n), B3_TPB, d_pks, n, (g1_jac*)ctx->g1j.p, d_st_key, 1);
+    }
+    LAUNCH_ON(s1, k_g1_jac_to_pp, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j.p, n, keys);
+    span_end(ctx, sp, s1);
+    if (!ctx->serial) {
+        cudaStream_t auxs[3] = {s0, s1, s2};
+        for (int k = 0; k < 3; k++) {
+            CK(cudaEventRecord(ctx->ev_join[k], auxs[k]));
+            CK(cudaStreamWaitEvent(sm, ctx->ev_join[k], 0));
+        }
+    }
+    CK(cudaEventRecord(ctx->ev[2], sm));
+    sp = span_begin(ctx, ST_FINAL_EXP, sm);
+    LAUNCH_ON(sm, k_items_finish, (unsigned)n, B3_COOP_THREADS, (const fp2*)ctx->lines.p, (const uint32_t*)ctx->qinf.p, (const g1_pp*)keys, n,
+              (const int32_t*)d_st_sig, (const int32_t*)d_st_key, (const int32_t*)ctx->ok.p, mode == B3_ITEM_VERIFY ? 0 : 1, d_accept, d_status, d_gt);
+    span_end(ctx, sp, sm);
+    CK(cudaEventRecord(ctx->ev[3], sm));
+    return B3_OK;
+}
+static int verify_batch_done(b3_ctx* ctx) {
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CKR(sync(ctx));
+    mark_collect(ctx);
+    cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev[0], ctx->ev[1]);
+    if (cudaEventElapsedTime(&ctx->last_ms[1], ctx->ev[2], ctx->ev[3]) != cudaSuccess) ctx->last_ms[1] = 0.f;
+    cudaGetLastError();
+    return B3_OK;
+}
+extern "C" int b3_verify_batch_dev(b3_ctx* ctx, int mode, const uint8_t* sigs192_dev, const uint8_t* pks96_dev, const uint32_t* pk_off_dev,
+                                   const uint8_t* msgs_dev, const uint32_t* msg_off_dev, size_t n, int32_t* accept_dev, int32_t* status_dev,
+                                   uint8_t* gt576_dev) {
+    CKR(begin(ctx));
+    if (n == 0) return B3_OK;
+    if (mode < B3_ITEM_VERIFY || mode > B3_ITEM_PRE_AGGREGATED || n > 0x3fffffffu) return B3_ERR_ARG;
+    if (!sigs192_dev || !pks96_dev || !msg_off_dev || !accept_dev || !status_dev || (mode == B3_ITEM_FAST_AGGREGATE && !pk_off_dev)) return B3_ERR_ARG;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    mark_reset(ctx);
+    size_t total_keys = n;
+    if (mode == B3_ITEM_FAST_AGGREGATE) {
+        uint32_t t = 0;
+        CK(cudaMemcpyAsync(&t, pk_off_dev + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CKR(sync(ctx));
+        total_keys = t;
+    }
+    CKR(verify_batch_core(ctx, mode, sigs192_dev, pks96_dev, pk_off_dev, total_keys, msgs_dev, msg_off_dev, n, accept_dev, status_dev, gt576_dev));
+    return verify_batch_done(ctx);
+}
+extern "C" int b3_verify_batch(b3_ctx* ctx, int mode, const uint8_t* sigs192, const uint8_t* pks96, const uint32_t* pk_off, const uint8_t* msgs,
+                               const uint32_t* msg_off, size_t n, int32_t* accept, int32_t* status, uint8_t* gt576) {
+    CKR(begin(ctx));
+    if (n == 0) return B3_OK;
+    if (mode < B3_ITEM_VERIFY || mode > B3_ITEM_PRE_AGGREGATED || n > 0x3fffffffu) return B3_ERR_ARG;
+    if (!sigs192 || !pks96 || !msg_off || !accept || !status || (mode == B3_ITEM_FAST_AGGREGATE && !pk_off)) return B3_ERR_ARG;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    mark_reset(ctx);
+    const size_t total_keys = mode == B3_ITEM_FAST_AGGREGATE ? pk_off[n] : n;
+    CKR(h2d(ctx, ctx->in_a, sigs192, 192 * n));
+    CKR(h2d(ctx, ctx->in_b, pks96, 96 * total_keys));
+    if (mode == B3_ITEM_FAST_AGGREGATE) CKR(h2d(ctx, ctx->in_e, pk_off, 4 * (n + 1)));
+    CKR(h2d(ctx, ctx->in_c, msgs, msg_off[n]));
+    CKR(h2d(ctx, ctx->in_d, msg_off, 4 * (n + 1)));
+    CKR(ensure(ctx, ctx->outb, (gt576 ? 576 * n : 0) + 8 * n + 16));
+    int32_t* d_accept = (int32_t*)ctx->outb.p;
+    int32_t* d_status = d_accept + n;
+    uint8_t* d_gt = gt576 ? (uint8_t*)(d_status + n) : nullptr;
+    CKR(verify_batch_core(ctx, mode, (const uint8_t*)ctx->in_a.p, (const uint8_t*)ctx->in_b.p, (const uint32_t*)ctx->in_e.p, total_keys,
+                          (const uint8_t*)ctx->in_c.p, (const uint32_t*)ctx->in_d.p, n, d_accept, d_status, d_gt));
+    CKR(d2h(ctx, accept, d_accept, 4 * n));
+    CKR(d2h(ctx, status, d_status, 4 * n));
+    if (gt576) CKR(d2h(ctx, gt576, d_gt, 576 * n));
+    return verify_batch_done(ctx);
+}
+
 // core of verify_multiple on device-resident inputs; leaves this rank's Miller product in *res and the first bad index in d_first_bad
 static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_t* d_pks, const uint32_t* d_pk_off, size_t total_keys,
                                 const uint8_t* d_msgs, const uint32_t* d_msg_off, const uint64_t* d_scalars, size_t n, long long index_base,

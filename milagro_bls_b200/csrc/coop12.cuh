@@ -130,6 +130,90 @@ COOP_FN void coop_miller_chain(fp12& f, const fp12* slots, coop_ws& ws) {
     coop_fp12_conj(f, f);
 }
 
+// ---- r = a * L for a line L = l0 + l3 w^3 + l5 w^5 (dense fp12 whose other coefficients are NOT read) ------------
+// r_k = a_k l0 + a_(k-3) l3 + a_(k-5) l5 with xi on the wrapped terms: 18 Fp2 products instead of 36.
+// phase 1: thread tid < 36 = (output coordinate c = 2k + comp, term t of {l0, l3, l5})
+B3_FN void coop_mul_line_p1(coop_ws& ws, const fp12& a, const fp12& l, int tid) {
+    if (tid >= 36) return;
+    const int c = tid / 3, t = tid - 3 * c, k = c >> 1, comp = c & 1;
+    const int j = t == 0 ? 0 : t == 1 ? 3 : 5;
+    int i = k - j;
+    const bool wrap = i < 0;
+    if (wrap) i += 6;
+    const fp2& x = coop_coef(a, i);
+    const fp2& y = coop_coef(l, j);
+    fp B0 = y.c0, B1 = y.c1;
+    if (wrap) {
+        fp_sub(B0, y.c0, y.c1);
+        fp_add(B1, y.c0, y.c1);
+    }
+    fp u2, v1, v2;
+    fp_neg(u2, x.c1);
+    fp_select(u2, comp != 0, x.c1, u2);
+    fp_select(v1, comp != 0, B1, B0);
+    fp_select(v2, comp != 0, B0, B1);
+    fp_mul2(ws.val[tid], x.c0, v1, u2, v2);
+}
+B3_FN void coop_mul_line_p2(fp12& r, const coop_ws& ws, int tid) {
+    if (tid >= 12) return;
+    fp acc = ws.val[3 * tid];
+    fp_add(acc, acc, ws.val[3 * tid + 1]);
+    fp_add(acc, acc, ws.val[3 * tid + 2]);
+    fp2& o = coop_coef(r, tid >> 1);
+    if (tid & 1) o.c1 = acc; else o.c0 = acc;
+}
+COOP_FN void coop_fp12_mul_line(fp12& r, const fp12& a, const fp12& l, coop_ws& ws) {
+    COOP_PHASE(coop_mul_line_p1(ws, a, l, tid));
+    COOP_PHASE(coop_mul_line_p2(r, ws, tid));
+}
+
+// ---- Miller product of the few pairs of ONE item, read straight from the line table of the split Miller loop --------
+// (batched per-item verification: Signature::verify / fast_aggregate_verify of many independent items, each with its own
+// final exponentiation -- the shape of A/pair.rs:313-405 `ate2`, one CTA per item).
+struct coop_item_pair {
+    size_t idx;            // pair index in the line table
+    fp ny, z3, xz;         // factors of the G1 member (g1_pp)
+    int valid;             // 0: a member is infinity, the pair contributes 1
+};
+// thread tid < 6 scales Fp coordinate tid of the unscaled line (u0, l3, u5) by its factor of P -> coefficient w^0 / w^3 / w^5
+B3_FN void coop_line_load_p(fp12& line, const fp2* src, const coop_item_pair& pr, int tid) {
+    if (tid >= 6) return;
+    const int h = tid >> 1;
+    const fp v = reinterpret_cast<const fp*>(src)[tid];
+    const fp f = h == 0 ? pr.ny : h == 1 ? pr.z3 : pr.xz;
+    fp r;
+    fp_mul(r, v, f);
+    fp2& o = coop_coef(line, h == 0 ? 0 : h == 1 ? 3 : 5);
+    if (tid & 1) o.c1 = r; else o.c0 = r;
+}
+B3_FN void coop_set_p(fp12& r, bool one, int tid) {      // r = 0 or 1
+    if (tid >= 12) return;
+    reinterpret_cast<fp*>(&r)[tid] = (one && tid == 0) ? FP_ONE : FP_NIL;
+}
+// f = conj( prod_pairs f_{|x|,Q}(P) ); `line` is scratch.  lines[(slot * n_pairs + idx) * 3 ..] as written by k_miller_lines.
+COOP_FN void coop_item_miller(fp12& f, fp12& line, coop_ws& ws, const fp2* lines, size_t n_pairs, const coop_item_pair* pr, int npr) {
+    const uint64_t x = B3_X_ABS;
+    bool have = false;                                   // uniform over the CTA
+    int a = B3_MILLER_DBL_SLOTS;
+    COOP_PHASE(coop_set_p(line, false, tid));
+    for (int it = 0; it < B3_MILLER_DBL_SLOTS; it++) {
+        if (have) coop_fp12_mul(f, f, f, ws);
+        const bool add = (x >> (62 - it)) & 1;
+        for (int s = 0; s < (add ? 2 : 1); s++) {
+            const size_t slot = s == 0 ? (size_t)it : (size_t)a;
+            for (int q = 0; q < npr; q++) {
+                if (!pr[q].valid) continue;
+                COOP_PHASE(coop_line_load_p(line, lines + (slot * n_pairs + pr[q].idx) * 3, pr[q], tid));
+                if (have) coop_fp12_mul_line(f, f, line, ws);
+                else { coop_fp12_copy(f, line); have = true; }
+            }
+        }
+        if (add) a++;
+    }
+    if (!have) COOP_PHASE(coop_set_p(f, true, tid));
+    coop_fp12_conj(f, f);
+}
+
 struct coop_fexp_ws {
     coop_ws ws;
     fp12 m, t, y0, y1, y2, y3, rr;

@@ -16,21 +16,6 @@
 #endif
 #define B3_LBH __launch_bounds__(B3_TPB, B3_MIN_CTAS)
 
-// G1 member of a pairing in the form the line scaling wants: for P = (X : Y : Z) Jacobian (x = X/Z^2, y = Y/Z^3)
-// the line  l0 = u0 (-y), l3, l5 = u5 x  times Z^3 is  u0 (-Y), l3 Z^3, u5 (X Z)  -- no inversion.
-struct g1_pp {
-    fp xz, ny, z3;
-    uint32_t inf;
-};
-B3_FN void g1_pp_from_jac(g1_pp& r, const g1_jac& p) {
-    fp z2;
-    fp_sqr(z2, p.z);
-    fp_mul(r.xz, p.x, p.z);
-    fp_neg(r.ny, p.y);
-    fp_mul(r.z3, z2, p.z);
-    r.inf = pt_is_inf(p) ? 1u : 0u;
-}
-
 // ------------------------------------------------------------------------------------------------ parsing
 // G1 uncompressed wire -> Jacobian (Z = 1, or infinity).  status: per-item AmclError code.
 __global__ void __launch_bounds__(B3_TPB) k_g1_parse(const uint8_t* __restrict__ in, size_t n, g1_jac* out, int32_t* status, int check_curve) {
@@ -758,6 +743,48 @@ __global__ void __launch_bounds__(B3_COOP_THREADS) k_final_exp(const fp12* in, u
         fp_raw_to_be(gt_wire + 48 * tid, t);
     }
     if (tid == 0) *is_one = fp12_is_one(s.rr) ? 1 : 0;
+}
+
+// ---- batched PER-ITEM verification (b3_verify_batch): one CTA per item ------------------------------------------------
+// Item i owns pairs i = (sig_i, -G1) and n + i = (H(msg_i), key_i) of a 2n-pair line table.  The CTA folds the 2 x 68
+// lines into its own accumulator (sparse cooperative products), runs its own final exponentiation and writes the
+// item's accept bit, status and (optionally) GT bytes -- the shape of `ate2` + `fexp` (A/pair.rs:313-541) per item.
+// Items the reference rejects before any pairing (bad encoding, subgroup check, empty / infinite aggregate key;
+// M/src/signature.rs:29-31, M/src/aggregates.rs:179-198,229-236) skip the arithmetic altogether.
+__global__ void __launch_bounds__(B3_COOP_THREADS) k_items_finish(const fp2* __restrict__ lines, const uint32_t* __restrict__ qinf,
+                                                                  const g1_pp* __restrict__ keys, size_t n, const int32_t* st_sig,
+                                                                  const int32_t* st_key, const int32_t* sig_ok, int reject_inf_key,
+                                                                  int32_t* accept, int32_t* status, uint8_t* gt_wire) {
+    __shared__ coop_fexp_ws s;
+    __shared__ fp12 line;
+    __shared__ coop_item_pair pr[2];
+    const size_t i = blockIdx.x;
+    const int code = st_sig[i] ? st_sig[i] : st_key[i];
+    const bool rejected = code != 0 || !sig_ok[i] || (reject_inf_key && keys[i].inf);
+    if (rejected) {                                    // uniform over the CTA
+        if (threadIdx.x == 0) { accept[i] = 0; status[i] = code; }
+        if (gt_wire) for (int b = threadIdx.x; b < 576; b += blockDim.x) gt_wire[576 * i + b] = 0;
+        return;
+    }
+    if (threadIdx.x == 0) {
+        pr[0].idx = i; pr[0].ny = G1_GEN_Y; pr[0].z3 = FP_ONE; pr[0].xz = G1_GEN_X;          // -G1: -(-y) = y
+        pr[0].valid = qinf[i] ? 0 : 1;
+        const g1_pp k = keys[i];
+        pr[1].idx = n + i; pr[1].ny = k.ny; pr[1].z3 = k.z3; pr[1].xz = k.xz;
+        pr[1].valid = (qinf[n + i] || k.inf) ? 0 : 1;
+    }
+    __syncthreads();
+    coop_item_miller(s.m, line, s.ws, lines, 2 * n, pr, 2);
+    coop_final_exp(s);
+    const int tid = (int)threadIdx.x;
+    if (gt_wire && tid < 12) {                        // wire order w^0, w^3, w^1, w^4, w^2, w^5, each (re, im)
+        const int order[6] = {0, 3, 1, 4, 2, 5};
+        const fp2& c = coop_coef(s.rr, order[tid >> 1]);
+        fp t;
+        fp_from_mont(t, (tid & 1) ? c.c1 : c.c0);
+        fp_raw_to_be(gt_wire + 576 * i + 48 * tid, t);
+    }
+    if (tid == 0) { accept[i] = fp12_is_one(s.rr) ? 1 : 0; status[i] = 0; }
 }
 
 // ------------------------------------------------------------------------------------------------ roofline microbenchmarks

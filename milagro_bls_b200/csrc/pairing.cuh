@@ -175,6 +175,21 @@ B3_FN void miller_start(miller_pt_t<F2>& t, const F2& X, const F2& Y, const F2& 
     t.y = Y;
     fp2_mul(t.z, z2, Z);
 }
+// G1 member of a pairing in the form the line scaling wants: for P = (X : Y : Z) Jacobian (x = X/Z^2, y = Y/Z^3)
+// the line  l0 = u0 (-y), l3, l5 = u5 x  times Z^3 is  u0 (-Y), l3 Z^3, u5 (X Z)  -- no inversion.
+struct g1_pp {
+    fp xz, ny, z3;
+    uint32_t inf;
+};
+B3_FN void g1_pp_from_jac(g1_pp& r, const g1_jac& p) {
+    fp z2;
+    fp_sqr(z2, p.z);
+    fp_mul(r.xz, p.x, p.z);
+    fp_neg(r.ny, p.y);
+    fp_mul(r.z3, z2, p.z);
+    r.inf = pt_is_inf(p) ? 1u : 0u;
+}
+
 // dense Fp12 value of a line  l0 + l3 w^3 + l5 w^5
 B3_FN void fp12_from_line(fp12& f, const fp2& l0, const fp2& l3, const fp2& l5) {
     f.c0.c0 = l0; fp2_zero(f.c0.c1); fp2_zero(f.c0.c2);

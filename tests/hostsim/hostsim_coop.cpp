@@ -91,4 +91,42 @@ int hc_multi_pairing_split(const uint8_t* q192s, const uint8_t* p96s, int n, uin
     fp12_to_wire(gt576, s.rr);
     return 0;
 }
+// Per-item path (k_items_finish): line table in the layout of k_miller_lines, then coop_item_miller (sparse cooperative
+// line products) and the cooperative final exponentiation -> GT bytes of prod_i e(Q_i, P_i).
+int hc_item_pairing(const uint8_t* q192s, const uint8_t* p96s, int n, uint8_t* gt576) {
+    static fp2 lines[B3_MILLER_SLOTS * 4 * 3];
+    static coop_item_pair pr[4];
+    static coop_fexp_ws s;
+    static fp12 line;
+    if (n > 4) return -1;
+    for (int i = 0; i < n; i++) {
+        g2_aff Q; g1_aff P; int e;
+        if ((e = g2_aff_from_wire(Q, q192s + 192 * i))) return e;
+        if ((e = g1_aff_from_wire(P, p96s + 96 * i))) return e;
+        pr[i].idx = (size_t)i;
+        pr[i].valid = !(Q.inf || P.inf);
+        g1_jac pj; pt_from_aff(pj, P);
+        g1_pp pp; g1_pp_from_jac(pp, pj);
+        pr[i].ny = pp.ny; pr[i].z3 = pp.z3; pr[i].xz = pp.xz;
+        if (!pr[i].valid) continue;
+        miller_pt_t<fp2> t, Qh;
+        fp2 one; fp2_one(one);
+        miller_start(t, Q.x, Q.y, one);
+        Qh = t;
+        int a = B3_MILLER_DBL_SLOTS;
+        for (int it = 0; it < B3_MILLER_DBL_SLOTS; it++) {
+            fp2* o = lines + ((size_t)it * n + i) * 3;
+            miller_dbl_step_u(t, o[0], o[1], o[2]);
+            if ((B3_X_ABS >> (62 - it)) & 1) {
+                o = lines + ((size_t)a * n + i) * 3;
+                miller_add_step_u(t, o[0], o[1], o[2], Qh.x, Qh.y, Qh.z);
+                a++;
+            }
+        }
+    }
+    coop_item_miller(s.m, line, s.ws, lines, (size_t)n, pr, n);
+    coop_final_exp(s);
+    fp12_to_wire(gt576, s.rr);
+    return 0;
+}
 }

@@ -468,6 +468,105 @@ def test_verify_multiple_large_batch_edge_sets(eng):
     assert not ok and fb == 377
 
 
+# ---------------------------------------------------------------- batched per-item verification (b3_verify_batch)
+def _batch_items():
+    """A mixed bag of items: (sig point, [key points], msg).  Valid, wrong message, wrong key, non-subgroup signature,
+    signature at infinity, key at infinity, keys summing to infinity, empty key list, ragged messages."""
+    sks, pks_o = _keys(5, base=4242)
+    items = []
+    for j, m in enumerate([b"", b"a", b"cats", bytes(range(32)), bytes(200)]):
+        ks = list(range(1 + j % 4))
+        sig = O.aggregate_signatures([O.sign(sks[k], m) for k in ks])
+        items.append((sig, [pks_o[k] for k in ks], m))
+    sig, ks, m = items[2]
+    items.append((sig, ks, b"dogs"))                                         # wrong message
+    items.append((sig, ks[:-1] + [pks_o[4]], m))                             # wrong key
+    items.append((O.map_to_curve_g2((5, 7)), ks, m))                         # on curve, not in G2
+    items.append((None, ks, m))                                              # signature at infinity
+    items.append((sig, [None], m))                                           # key at infinity
+    items.append((None, [O.sk_to_pk(1), O.sk_to_pk(O.r - 1)], m))            # keys sum to infinity, sig = infinity
+    items.append((sig, [], m))                                               # no keys
+    return items
+
+
+def test_verify_batch_fast_aggregate(eng):
+    from milagro_bls_b200 import _lib
+    items = _batch_items()
+    sigs = b"".join(g2w(s) for s, _, _ in items)
+    pks = b"".join(g1w(P) for _, ks, _ in items for P in ks)
+    off = np.cumsum([0] + [len(ks) for _, ks, _ in items]).astype(np.uint32)
+    acc, st, gt = eng.verify_batch(_lib.ITEM_FAST_AGGREGATE, sigs, pks, off, [m for _, _, m in items], want_gt=True)
+    n_acc = 0
+    for i, (sig, ks, m) in enumerate(items):
+        ok_o, gt_o = O.fast_aggregate_verify(sig, m, ks, want_gt=True)
+        assert bool(acc[i]) == ok_o, i
+        assert st[i] == (-1 if len(ks) == 0 else 0), i
+        assert gt[i].tobytes() == (O.f12_to_bytes(gt_o) if gt_o is not None else bytes(576)), i
+        # and the single-item entry point agrees
+        assert eng.fast_aggregate_verify(g2w(sig), b"".join(g1w(P) for P in ks), m) == ok_o
+        n_acc += ok_o
+    assert n_acc == 5
+    # without GT, and serialised stages: same bits
+    acc2, st2 = eng.verify_batch(_lib.ITEM_FAST_AGGREGATE, sigs, pks, off, [m for _, _, m in items])
+    eng.set_serial(True)
+    acc3, _ = eng.verify_batch(_lib.ITEM_FAST_AGGREGATE, sigs, pks, off, [m for _, _, m in items])
+    eng.set_serial(False)
+    assert list(acc2) == list(acc) and list(acc3) == list(acc) and list(st2) == list(st)
+
+
+def test_verify_batch_single_key_modes(eng):
+    from milagro_bls_b200 import _lib
+    items = [(s, ks, m) for s, ks, m in _batch_items() if len(ks) == 1]
+    sk = 77
+    items.append((O.sign(sk, b"x"), [O.sk_to_pk(sk)], b"x"))
+    items.append((O.G2_GEN, [None], b"m"))                                   # Signature::verify does not reject pk = infinity
+    sigs = b"".join(g2w(s) for s, _, _ in items)
+    pks = b"".join(g1w(ks[0]) for _, ks, _ in items)
+    msgs = [m for _, _, m in items]
+    acc, st, gt = eng.verify_batch(_lib.ITEM_VERIFY, sigs, pks, None, msgs, want_gt=True)
+    acc_p, st_p, gt_p = eng.verify_batch(_lib.ITEM_PRE_AGGREGATED, sigs, pks, None, msgs, want_gt=True)
+    assert not st.any() and not st_p.any()
+    for i, (sig, ks, m) in enumerate(items):
+        ok_o, gt_o = O.signature_verify(sig, m, ks[0], want_gt=True)
+        assert bool(acc[i]) == ok_o and gt[i].tobytes() == (O.f12_to_bytes(gt_o) if gt_o is not None else bytes(576)), i
+        ok_o, gt_o = O.fast_aggregate_verify_pre_aggregated(sig, m, ks[0], want_gt=True)
+        assert bool(acc_p[i]) == ok_o and gt_p[i].tobytes() == (O.f12_to_bytes(gt_o) if gt_o is not None else bytes(576)), i
+    # malformed inputs are reported per item and do not disturb their neighbours
+    bad_sig = bytearray(sigs); bad_sig[192 * 1 + 100] ^= 1                    # item 1: signature off the curve
+    bad_pk = bytearray(pks); bad_pk[96 * 2 + 50] ^= 1                         # item 2: key off the curve
+    acc_b, st_b = eng.verify_batch(_lib.ITEM_VERIFY, bytes(bad_sig), bytes(bad_pk), None, msgs)
+    assert st_b[1] == -5 and st_b[2] == -5 and not acc_b[1] and not acc_b[2]
+    keep = [i for i in range(len(items)) if i not in (1, 2)]
+    assert [bool(acc_b[i]) for i in keep] == [bool(acc[i]) for i in keep] and not st_b[keep].any()
+    # empty batch
+    a0, s0 = eng.verify_batch(_lib.ITEM_VERIFY, b"", b"", None, [])
+    assert len(a0) == 0 and len(s0) == 0
+
+
+def test_verify_batch_locates_bad_set_after_batch_reject(eng):
+    """The use the reference's callers make of per-item bits: verify_multiple rejects, the batch call names the culprit."""
+    from milagro_bls_b200 import _lib
+    import milagro_bls_b200 as mb
+    rnd = random.Random(21)
+    n, bad = 700, 123
+    sks = [rnd.randrange(1, O.r) for _ in range(n)]
+    pk = eng.g1_mul_gen(sks)
+    msgs = [bytes(rnd.getrandbits(8) for _ in range(32)) for _ in range(n)]
+    sig = eng.g2_mul(eng.hash_to_g2(msgs).reshape(-1), sks)
+    msgs[bad] = b"tampered" + msgs[bad][8:]
+    rng = mb.SeededRng(b"locate")
+    scalars = np.array([mb.draw_scalar(rng) for _ in range(n)], dtype=np.uint64)
+    moff = list(range(0, 32 * n + 1, 32))
+    ok, fb = eng.verify_multiple(sig.reshape(-1), pk.reshape(-1), None, b"".join(msgs), moff, scalars)
+    assert not ok and fb == -1
+    acc, st, gt = eng.verify_batch(_lib.ITEM_PRE_AGGREGATED, sig.reshape(-1), pk.reshape(-1), None, msgs, want_gt=True)
+    assert not st.any() and list(np.nonzero(~acc)[0]) == [bad]
+    one = O.f12_to_bytes(O.F12_ONE)
+    assert all(gt[i].tobytes() == one for i in range(n) if i != bad)
+    ok_o, gt_o = O.fast_aggregate_verify_pre_aggregated(O.deserialize_g2(sig[bad].tobytes()), msgs[bad], O.sk_to_pk(sks[bad]), want_gt=True)
+    assert not ok_o and gt[bad].tobytes() == O.f12_to_bytes(gt_o)
+
+
 def test_imad_probe_runs(eng):
     assert eng.imad_peak(False) > 1e12
     assert eng.imad_peak(True) > 1e11

@@ -303,6 +303,23 @@ def test_split_miller_loop(hc):
     assert hc.hc_multi_pairing_split(g2w(None) + g2w(H), g1w(pk) + g1w(None), 2, gt) == 0 and gt.raw == O.f12_to_bytes(O.F12_ONE)
 
 
+def test_item_pairing(hc):
+    """Per-item path of b3_verify_batch: sparse cooperative line products straight from the line table."""
+    gt = ctypes.create_string_buffer(576)
+    sk, msg = 0x1234567890abcdef, b"cats"
+    pk, H = O.sk_to_pk(sk), O.hash_to_curve_g2(msg)
+    sig = O.g2_mul(H, sk)
+    ps = g1w(O.NEG_G1) + g1w(pk)
+    assert hc.hc_item_pairing(g2w(sig) + g2w(H), ps, 2, gt) == 0 and gt.raw == O.f12_to_bytes(O.F12_ONE)
+    H2 = O.hash_to_curve_g2(b"dogs")
+    assert hc.hc_item_pairing(g2w(sig) + g2w(H2), ps, 2, gt) == 0
+    assert gt.raw == O.f12_to_bytes(O.fexp(O.ate2(sig, O.NEG_G1, H2, pk)))
+    # an infinite member contributes one; a single live pair; no live pair at all
+    assert hc.hc_item_pairing(g2w(None) + g2w(H2), ps, 2, gt) == 0
+    assert gt.raw == O.f12_to_bytes(O.fexp(O.ate2(H2, pk, None, None)))
+    assert hc.hc_item_pairing(g2w(None) + g2w(H), g1w(pk) + g1w(None), 2, gt) == 0 and gt.raw == O.f12_to_bytes(O.F12_ONE)
+
+
 def test_fp_mul2(hc):
     edge = [0, 1, p - 1, p - 2, (1 << 380), p >> 1]
     cases = [(rfp(), rfp(), rfp(), rfp()) for _ in range(200)]
