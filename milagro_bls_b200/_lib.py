@@ -48,6 +48,7 @@ def lib():
         "b3_stage_name": ([ctypes.c_int], ctypes.c_char_p),
         "b3_stage_count": ([], ctypes.c_int),
         "b3_ctx_set_serial": ([vp, ctypes.c_int], None),
+        "b3_ctx_set_item_kernel": ([vp, ctypes.c_int], None),
         "b3_g1_decompress": ([vp, u8p, sz, ctypes.c_int, u8p, i32p], ctypes.c_int),
         "b3_g2_decompress": ([vp, u8p, sz, u8p, i32p], ctypes.c_int),
         "b3_g1_compress": ([vp, u8p, sz, u8p, i32p], ctypes.c_int),
@@ -83,7 +84,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "b3_ctx_create", "b3_ctx_destroy", "b3_last_error", "b3_ctx_stream", "b3_ctx_launch_count", "b3_ctx_last_kernel_ms",
-    "b3_ctx_stage_ms", "b3_stage_name", "b3_stage_count", "b3_ctx_set_serial",
+    "b3_ctx_stage_ms", "b3_stage_name", "b3_stage_count", "b3_ctx_set_serial", "b3_ctx_set_item_kernel",
     "b3_g1_decompress", "b3_g2_decompress", "b3_g1_compress", "b3_g2_compress", "b3_g1_validate", "b3_g2_subgroup_check",
     "b3_g1_aggregate", "b3_g2_aggregate", "b3_hash_to_g2", "b3_verify", "b3_fast_aggregate_verify",
     "b3_fast_aggregate_verify_pre_aggregated", "b3_aggregate_verify", "b3_verify_multiple",

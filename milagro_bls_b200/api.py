@@ -96,6 +96,10 @@ class Engine:
         """serial=True: independent stages run one after another (per-stage timing); False: overlapped (default)."""
         self.L.b3_ctx_set_serial(self.handle, 1 if serial else 0)
 
+    def set_item_kernel(self, which=0):
+        """Finishing kernel of verify_batch: 0 = by batch size, 1 = one CTA per item, 2 = one thread per item."""
+        self.L.b3_ctx_set_item_kernel(self.handle, int(which))
+
     def stage_ms(self):
         """{stage name: device ms} of the most recent verification / hash call (CUDA events on the library's stream)."""
         return {self.L.b3_stage_name(i).decode(): float(self.L.b3_ctx_stage_ms(self.handle, i)) for i in range(self.L.b3_stage_count())}

@@ -46,6 +46,7 @@ struct b3_ctx {
     cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_fork2 = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     int serial = 0;
+    int item_kernel = 0;            // b3_verify_batch finishing kernel: 0 = by batch size, 1 = CTA per item, 2 = thread per item
     // scratch (grown on demand, reused across calls)
     dev_buf in_a, in_b, in_c, in_d, in_e, in_f;      // staged host inputs
     dev_buf g1j, g1j2, g1a, g2a_sig, g2j, g2j2, g2j_h, g2a, g2q, g1pp, qinf, f12a, f12b, lines, status, ok, misc, outb;
@@ -143,6 +144,7 @@ extern "C" float b3_ctx_stage_ms(b3_ctx* ctx, int stage) { return (ctx && stage 
 extern "C" const char* b3_stage_name(int stage) { return (stage >= 0 && stage < B3_N_STAGES) ? kStageNames[stage] : ""; }
 extern "C" int b3_stage_count(void) { return B3_N_STAGES - 1; }
 extern "C" void b3_ctx_set_serial(b3_ctx* ctx, int serial) { if (ctx) ctx->serial = serial; }
+extern "C" void b3_ctx_set_item_kernel(b3_ctx* ctx, int which) { if (ctx) ctx->item_kernel = which; }
 static void mark_reset(b3_ctx* ctx) { ctx->n_spans = 0; }
 // open a stage span on `strm`; returns the span index (or -1 when the table is full)
 static int span_begin(b3_ctx* ctx, int id, cudaStream_t strm) {
@@ -610,6 +612,7 @@ extern "C" int b3_aggregate_verify(b3_ctx* ctx, const uint8_t sig192[192], const
 }
 
 // ---- batched per-item verification: n independent items, one accept bit each ------------------------
+#define B3_ITEMS_THREAD_MIN 4096
 static int verify_batch_core(b3_ctx* ctx, int mode, const uint8_t* d_sigs, const uint8_t* d_pks, const uint32_t* d_pk_off, size_t total_keys,
                              const uint8_t* d_msgs, const uint32_t* d_msg_off, size_t n, int32_t* d_accept, int32_t* d_status, uint8_t* d_gt) {
     CKR(ensure(ctx, ctx->g2a_sig, sizeof(g2_aff) * n));
@@ -670,8 +673,16 @@ static int verify_batch_core(b3_ctx* ctx, int mode, const uint8_t* d_sigs, const
     }
     CK(cudaEventRecord(ctx->ev[2], sm));
     sp = span_begin(ctx, ST_FINAL_EXP, sm);
-    LAUNCH_ON(sm, k_items_finish, (unsigned)n, B3_COOP_THREADS, (const fp2*)ctx->lines.p, (const uint32_t*)ctx->qinf.p, (const g1_pp*)keys, n,
-              (const int32_t*)d_st_sig, (const int32_t*)d_st_key, (const int32_t*)ctx->ok.p, mode == B3_ITEM_VERIFY ? 0 : 1, d_accept, d_status, d_gt);
+    // CTA per item: ~1.5 ms per wave of 2 x 148 items; thread per item: one item's latency (~20 ms) for any batch that fits the
+    // machine -- the crossover is near 4 k items
+    const bool per_thread = ctx->item_kernel == 2 || (ctx->item_kernel == 0 && n >= B3_ITEMS_THREAD_MIN);
+    if (per_thread)
+        LAUNCH_ON(sm, k_items_finish_t, (unsigned)((n + B3_ITEMS_TPB - 1) / B3_ITEMS_TPB), B3_ITEMS_TPB, (const fp2*)ctx->lines.p,
+                  (const uint32_t*)ctx->qinf.p, (const g1_pp*)keys, n, (const int32_t*)d_st_sig, (const int32_t*)d_st_key,
+                  (const int32_t*)ctx->ok.p, mode == B3_ITEM_VERIFY ? 0 : 1, d_accept, d_status, d_gt);
+    else
+        LAUNCH_ON(sm, k_items_finish, (unsigned)n, B3_COOP_THREADS, (const fp2*)ctx->lines.p, (const uint32_t*)ctx->qinf.p, (const g1_pp*)keys, n,
+                  (const int32_t*)d_st_sig, (const int32_t*)d_st_key, (const int32_t*)ctx->ok.p, mode == B3_ITEM_VERIFY ? 0 : 1, d_accept, d_status, d_gt);
     span_end(ctx, sp, sm);
     CK(cudaEventRecord(ctx->ev[3], sm));
     return B3_OK;

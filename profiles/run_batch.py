@@ -1,5 +1,5 @@
 """Timing helper for b3_verify_batch (per-item accept bits): n items, device-resident inputs, CUDA-event time of the call.
-usage: python profiles/run_batch.py [n_items] [keys_per_item] [reps]"""
+usage: python profiles/run_batch.py [n_items] [keys_per_item] [reps] [item_kernel: 0 auto, 1 CTA per item, 2 thread per item]"""
 import os
 import sys
 import random
@@ -15,6 +15,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 k = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 eng = mb.Engine(0)
+eng.set_item_kernel(int(sys.argv[4]) if len(sys.argv) > 4 else 0)
 rnd = random.Random(1)
 R = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
 pool = 4096

@@ -489,7 +489,15 @@ def _batch_items():
     return items
 
 
-def test_verify_batch_fast_aggregate(eng):
+@pytest.fixture(params=[1, 2], ids=["cta_per_item", "thread_per_item"])
+def item_kernel(eng, request):
+    """Both finishing kernels of b3_verify_batch on the same small batches (the default picks by batch size)."""
+    eng.set_item_kernel(request.param)
+    yield request.param
+    eng.set_item_kernel(0)
+
+
+def test_verify_batch_fast_aggregate(eng, item_kernel):
     from milagro_bls_b200 import _lib
     items = _batch_items()
     sigs = b"".join(g2w(s) for s, _, _ in items)
@@ -514,7 +522,7 @@ def test_verify_batch_fast_aggregate(eng):
     assert list(acc2) == list(acc) and list(acc3) == list(acc) and list(st2) == list(st)
 
 
-def test_verify_batch_single_key_modes(eng):
+def test_verify_batch_single_key_modes(eng, item_kernel):
     from milagro_bls_b200 import _lib
     items = [(s, ks, m) for s, ks, m in _batch_items() if len(ks) == 1]
     sk = 77
