@@ -5,11 +5,13 @@ Contract (see the task statement):  python bench.py --gpus N --steps K --warmup 
   * workload at N = 1: BASELINE.json configs[3] -- 8192 attestation sets x 128 public keys, distinct random
     32-byte messages, 63-bit batch scalars (C4).  For N > 1 every rank keeps 8192 sets (weak scaling), so N = 8
     is BASELINE.json configs[4] (2^16 sets, NCCL combine of the 592-byte partial Miller products).
-  * a step = one full verification of the batch: G2 subgroup checks, G1 key aggregation, [c]apk, hash_to_G2,
-    [c]sig sum, n+1 Miller loops, Fp12 product, (all-gather,) one final exponentiation, accept bit.
-  * value  = sets verified per second, inputs resident in HBM (device-pointer C-ABI entry points), with --inflight
-             (default 2) batches in flight per GPU: one b3_ctx + one host thread per batch, the reference's own
-             threading model (re-entrant types, callers parallelise externally).  K steps = K full verifications.
+  * one call = one full verification of a C4 batch: G2 subgroup checks, G1 key aggregation, [c]apk, hash_to_G2,
+    [c]sig sum, n+8 Miller loops, Fp12 product, (all-gather,) one final exponentiation, accept bit.
+  * a step = one such call on EACH of --inflight (default 6) contexts per GPU, running concurrently: one b3_ctx + one
+    host thread per call, the reference's own threading model (re-entrant types, callers parallelise externally).  A
+    single 8192-set call is a chain of latency-bound kernels (~7 ms end to end) that cannot fill 148 SMs by itself;
+    K steps = K x inflight full verifications of 8192 sets each.
+  * value  = sets verified per second, inputs resident in HBM (device-pointer C-ABI entry points).
              `one_batch_in_flight` reports the same metric with a single call at a time (call latency).
   * e2e    = same metric through the host-pointer C-ABI call (b3_verify_multiple) with pinned HOST buffers:
              H2D of the step's inputs and D2H of accept + GT inside the timed region.
@@ -22,6 +24,9 @@ Only this file's cpu_baseline / --impl reference legs touch oracle/ -- never the
 import argparse
 import json
 import os
+# every context owns four CUDA streams; the default of 8 hardware work queues would alias the streams of concurrent
+# batches onto shared queues (false dependencies between independent batches)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import subprocess
 import sys
 import threading
@@ -178,7 +183,7 @@ def main():
     ap.add_argument("--ref-sets", type=int, default=2048,
                     help="sets per step of the CPU reference arm / cpu_baseline sample (~20 s of CPU work on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=2,
+    ap.add_argument("--inflight", type=int, default=6,
                     help="verification batches in flight per GPU (one b3_ctx + host thread each; 1 = one call at a time)")
     ap.add_argument("--h2c-msgs", type=int, default=65536, help="messages per hash_to_G2 batch of the second metric")
     ap.add_argument("--breakdown", action="store_true", help="print the per-stage device times to stderr")
@@ -295,14 +300,18 @@ def _bench_lanes(eng, lanes, args, world, rank, local_rank, dev):
         torch.cuda.synchronize()
 
     def run_steps(steps, use_lanes, host_inputs, flush_l2):
-        """`steps` full verifications, step i on lane i % len(use_lanes); up to len(use_lanes) batches are in flight.  Lane threads
-        produce the per-rank partial Miller products; this thread consumes them IN STEP ORDER (so the collectives are issued in
-        the same order on every rank): all-gather (N > 1), product, final exponentiation, accept bit."""
+        """`steps` steps; a step = ONE full verification of a C4-shaped batch ON EVERY LANE (len(use_lanes) concurrent calls, each
+        on its own context and host thread), so steps * len(use_lanes) batches in all, batch i on lane i % L.
+        N = 1: the lane thread runs the whole call (device-pointer partial + combine on its own context, or the host-pointer
+        b3_verify_multiple).  N > 1: lane threads produce the per-rank partial Miller products; this thread consumes them IN
+        BATCH ORDER (so the collectives are issued in the same order on every rank): all-gather, product, final exponentiation,
+        accept bit."""
         L = len(use_lanes)
-        partials = torch.zeros(max(steps, 1), PB, dtype=torch.uint8, device=dev)
+        B = steps * L
+        partials = torch.zeros(max(B, 1), PB, dtype=torch.uint8, device=dev)
         torch.cuda.current_stream().synchronize()
-        ready = [threading.Event() for _ in range(steps)]
-        results = [None] * steps
+        ready = [threading.Event() for _ in range(B)]
+        results = [None] * B
         errors = []
         full_call = host_inputs and world == 1             # the reference-facing call: b3_verify_multiple on host pointers
 
@@ -310,7 +319,7 @@ def _bench_lanes(eng, lanes, args, world, rank, local_rank, dev):
             ln = use_lanes[t]
             try:
                 with torch.cuda.stream(ln.stream):
-                    for i in range(t, steps, L):
+                    for i in range(t, B, L):
                         if flush_l2:
                             flush.fill_(1)                          # evict L2 between iterations (single-lane mode only)
                             ln.stream.synchronize()
@@ -319,13 +328,17 @@ def _bench_lanes(eng, lanes, args, world, rank, local_rank, dev):
                             ok, fb, _gt = ln.eng.verify_multiple(p["sigs"].numpy(), p["pks"].numpy(), p["pk_off"].numpy(), p["msgs"].numpy(),
                                                                  p["msg_off"].numpy(), p["scal"].numpy().view(np.uint64), want_gt=True)
                             results[i] = (ok, fb)
+                            add_stages(ln.eng)
                         else:
                             if host_inputs:
                                 for k in ln.pin:
                                     ln.d[k].copy_(ln.pin[k], non_blocking=True)
                                 ln.stream.synchronize()
                             ln.partial_dev(n, base, partials[i].data_ptr())
-                        add_stages(ln.eng)
+                            add_stages(ln.eng)
+                            if world == 1:
+                                results[i] = ln.eng.combine_partials_dev(partials[i].data_ptr(), 1)
+                                add_stages(ln.eng)
                         ready[i].set()
             except BaseException as ex:                              # noqa: BLE001
                 errors.append(ex)
@@ -335,18 +348,15 @@ def _bench_lanes(eng, lanes, args, world, rank, local_rank, dev):
         threads = [threading.Thread(target=lane_main, args=(t,), daemon=True) for t in range(L)]
         for th in threads:
             th.start()
-        for i in range(steps):
+        for i in range(B):
             ready[i].wait()
             if errors:
                 break
-            if full_call:
+            if world == 1:
                 continue
-            if world > 1:
-                g = sharding.all_gather_partials(partials[i], world)      # the ONLY collective: world x 592 bytes over NCCL
-                torch.cuda.current_stream().synchronize()
-                results[i] = eng.combine_partials_dev(g.data_ptr(), world)
-            else:
-                results[i] = eng.combine_partials_dev(partials[i].data_ptr(), 1)
+            g = sharding.all_gather_partials(partials[i], world)      # the ONLY collective: world x 592 bytes over NCCL
+            torch.cuda.current_stream().synchronize()
+            results[i] = eng.combine_partials_dev(g.data_ptr(), world)
             add_stages(eng)
         for th in threads:
             th.join()
@@ -358,7 +368,7 @@ def _bench_lanes(eng, lanes, args, world, rank, local_rank, dev):
         return eng.launches + sum(ln.eng.launches for ln in lanes)
 
     def timed(steps, warmup, use_lanes, host_inputs=False, flush_l2=False):
-        for r in run_steps(max(warmup, len(use_lanes)), use_lanes, host_inputs, flush_l2):
+        for r in run_steps(warmup, use_lanes, host_inputs, flush_l2):
             assert r[0] and r[1] == -1, "verification of the valid synthetic batch must accept"
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -377,7 +387,7 @@ def _bench_lanes(eng, lanes, args, world, rank, local_rank, dev):
         for r in res:
             assert r[0] and r[1] == -1, "verification of the valid synthetic batch must accept"
         with stage_lock:
-            st = {k: v / steps for k, v in stage_acc.items()}
+            st = {k: v / (steps * len(use_lanes)) for k, v in stage_acc.items()}
         return float(t.item()), total_launches() - launches0, st, res[-1]
 
     W = max(args.warmup, 3)
@@ -437,9 +447,9 @@ def _bench_lanes(eng, lanes, args, world, rank, local_rank, dev):
     ms_h2c = float(t.item())
     h2c_rate = nh * world * args.steps / (ms_h2c * 1e-3)
 
-    total_sets = n * world
-    value = total_sets * args.steps / (ms_res * 1e-3)
-    e2e = total_sets * args.steps / (ms_e2e * 1e-3)
+    total_sets = n * world                               # per call across the ranks
+    value = total_sets * S * args.steps / (ms_res * 1e-3)
+    e2e = total_sets * S * args.steps / (ms_e2e * 1e-3)
     h2d_bytes = lanes[0].h2d_bytes
 
     if rank == 0:
@@ -459,7 +469,7 @@ def _bench_lanes(eng, lanes, args, world, rank, local_rank, dev):
                          "frac_timed_region": FP_MULS[k] * MACS_PER_FP_MUL * n / (stages[k] * 1e-3) / peak_mac,
                          "frac_alone": FP_MULS[k] * MACS_PER_FP_MUL * n / (stages_serial[k] * 1e-3) / peak_mac if stages_serial.get(k) else None}
                      for k in stages if FP_MULS.get(k, 0) > 0 and stages[k] > 0}
-        step_ms = ms_res / args.steps
+        step_ms = ms_res / (args.steps * S)            # device time per 8192-set call in the headline region
         whole = FP_MULS_PER_SET * MACS_PER_FP_MUL * n / (step_ms * 1e-3)
         whole_one = FP_MULS_PER_SET * MACS_PER_FP_MUL * n / (ms_one / args.steps * 1e-3)
         try:
@@ -503,11 +513,13 @@ def _bench_lanes(eng, lanes, args, world, rank, local_rank, dev):
                "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_res / args.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (12x32-bit Montgomery limbs, IMAD.WIDE)",
                "data": "synthetic",
-               "config": {"workload": f"verify_multiple_aggregate_signatures: {n} sets x {nk} keys per GPU "
-                                      f"({'C4' if world == 1 else 'C5-style'}: {total_sets} sets total per step), 32-byte distinct messages, 63-bit scalars",
-                          "sets_per_gpu": n, "keys_per_set": nk, "total_sets": total_sets, "parallelism": f"set-sharded x{world}",
+               "config": {"workload": f"verify_multiple_aggregate_signatures: calls of {n} sets x {nk} keys per GPU "
+                                      f"({'C4' if world == 1 else 'C5-style'}: {total_sets} sets per call over {world} GPU(s)), 32-byte distinct "
+                                      f"messages, 63-bit scalars; a step = {S} such calls in flight per GPU on {S} contexts",
+                          "sets_per_call_per_gpu": n, "keys_per_set": nk, "sets_per_call": total_sets, "calls_per_step": S,
+                          "sets_per_step": total_sets * S, "parallelism": f"set-sharded x{world}",
                           "batches_in_flight": S, "cache": cache},
-               "e2e": {"value": e2e, "unit": "sets/s", "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": (576 + 16) * world,
+               "e2e": {"value": e2e, "unit": "sets/s", "h2d_bytes_per_step": h2d_bytes * world * S, "d2h_bytes_per_step": (576 + 16) * world * S,
                        "ms_per_step": ms_e2e / args.steps},
                "one_batch_in_flight": {"value": total_sets * args.steps / (ms_one * 1e-3), "ms_per_step": ms_one / args.steps,
                                        "e2e_value": total_sets * args.steps / (ms_one_e2e * 1e-3), "e2e_ms_per_step": ms_one_e2e / args.steps,

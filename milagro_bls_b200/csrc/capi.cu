@@ -43,8 +43,8 @@ struct b3_ctx {
     int n_spans = 0;
     float stage_ms[B3_N_STAGES];
     // independent stages of verify_multiple run concurrently on aux streams (fork/join by events) unless serial != 0
-    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_fork2 = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_fork2 = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
     int serial = 0;
     int item_kernel = 0;            // b3_verify_batch finishing kernel: 0 = by batch size, 1 = CTA per item, 2 = thread per item
     // scratch (grown on demand, reused across calls)
@@ -101,14 +101,17 @@ extern "C" int b3_ctx_create(int device, b3_ctx** out) {
     if (cudaSetDevice(device) != cudaSuccess) return B3_ERR_CUDA;
     b3_ctx* ctx = new b3_ctx();
     ctx->device = device;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B3_ERR_CUDA; }
-    for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
-    for (int i = 0; i < B3_MAX_MARKS; i++) { cudaEventCreate(&ctx->span_a[i]); cudaEventCreate(&ctx->span_b[i]); }
+    // Priorities (lower number = served first): the context's own stream carries the END of every call (Miller
+    // accumulation, closing chain, final exponentiation -- single-CTA kernels that must not queue behind the wide kernels
+    // of other contexts' batches), aux[2] the longest dependent chain of a batch (hash_to_G2 -> Miller point chains).
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    for (int i = 0; i < 3; i++) {
-        // aux[2] carries the longest dependent chain of a batch (hash_to_G2 -> Miller point chains): highest priority
-        if (cudaStreamCreateWithPriority(&ctx->aux[i], cudaStreamNonBlocking, i == 2 ? prio_hi : prio_lo) != cudaSuccess) { delete ctx; return B3_ERR_CUDA; }
+    const int prio_mid = prio_hi < prio_lo ? prio_hi + 1 : prio_hi;
+    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete ctx; return B3_ERR_CUDA; }
+    for (int i = 0; i < 4; i++) cudaEventCreate(&ctx->ev[i]);
+    for (int i = 0; i < B3_MAX_MARKS; i++) { cudaEventCreate(&ctx->span_a[i]); cudaEventCreate(&ctx->span_b[i]); }
+    for (int i = 0; i < 4; i++) {
+        if (cudaStreamCreateWithPriority(&ctx->aux[i], cudaStreamNonBlocking, i == 2 ? prio_mid : prio_lo) != cudaSuccess) { delete ctx; return B3_ERR_CUDA; }
         cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
@@ -130,7 +133,7 @@ extern "C" void b3_ctx_destroy(b3_ctx* ctx) {
     if (ctx->d_dst) cudaFree(ctx->d_dst);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < B3_MAX_MARKS; i++) { cudaEventDestroy(ctx->span_a[i]); cudaEventDestroy(ctx->span_b[i]); }
-    for (int i = 0; i < 3; i++) { cudaStreamSynchronize(ctx->aux[i]); cudaStreamDestroy(ctx->aux[i]); cudaEventDestroy(ctx->ev_join[i]); }
+    for (int i = 0; i < 4; i++) { cudaStreamSynchronize(ctx->aux[i]); cudaStreamDestroy(ctx->aux[i]); cudaEventDestroy(ctx->ev_join[i]); }
     cudaEventDestroy(ctx->ev_fork);
     cudaEventDestroy(ctx->ev_fork2);
     cudaStreamDestroy(ctx->stream);
@@ -200,11 +203,12 @@ static int fp12_product(b3_ctx* ctx, fp12* a, fp12* b, size_t n, fp12** res) {
     *res = src;
     return B3_OK;
 }
-static int g2_sum(b3_ctx* ctx, g2_jac* a, g2_jac* b, size_t n, g2_jac** res) {
+static int g2_sum(b3_ctx* ctx, g2_jac* a, g2_jac* b, size_t n, g2_jac** res, cudaStream_t strm = nullptr) {
     g2_jac *src = a, *dst = b;
+    if (!strm) strm = ctx->stream;
     while (n > 1) {
         size_t m = (n + 1) / 2;
-        LAUNCH(k_g2_add_pairs, nblk(2 * m), B3_TPB, src, n, dst);
+        LAUNCH_ON(strm, k_g2_add_pairs, nblk(2 * m), B3_TPB, src, n, dst);
         g2_jac* t = src; src = dst; dst = t;
         n = m;
     }
@@ -765,11 +769,13 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
     CKR(miller_reserve(ctx, n_total));
     if (n > 0) {
         CKR(ensure(ctx, ctx->g2j, sizeof(g2_jac) * (n + 1)));
-        // The four stages below are independent of each other; unless ctx->serial they run concurrently:
-        //   main : parse signatures -> S = sum_j [c_j] sig_j            aux0 : subgroup checks of the parsed signatures
-        //   aux1 : aggregate keys -> P_j = [c_j] apk_j                  aux2 : H_j = hash_to_curve_g2(msg_j)
+        // The stages below are independent of each other; unless ctx->serial they run concurrently:
+        //   main : parse signatures (... and, after the join, the end of the call: accumulation, closing chain)
+        //   aux0 : subgroup checks of the parsed signatures               aux1 : aggregate keys -> P_j = [c_j] apk_j
+        //   aux2 : H_j = hash_to_curve_g2(msg_j) -> their point chains    aux3 : S = sum_j [c_j] sig_j -> its point chains
         cudaStream_t sm = ctx->stream;
         cudaStream_t s0 = ctx->serial ? sm : ctx->aux[0], s1 = ctx->serial ? sm : ctx->aux[1], s2 = ctx->serial ? sm : ctx->aux[2];
+        cudaStream_t s3 = ctx->serial ? sm : ctx->aux[3];
         int sp;
         if (!ctx->serial) {
             CK(cudaEventRecord(ctx->ev_fork, sm));
@@ -789,6 +795,7 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
         if (!ctx->serial) {
             CK(cudaEventRecord(ctx->ev_fork2, sm));
             CK(cudaStreamWaitEvent(s0, ctx->ev_fork2, 0));
+            CK(cudaStreamWaitEvent(s3, ctx->ev_fork2, 0));
         }
         sp = span_begin(ctx, ST_SIG_CHECK, s0);
         LAUNCH_ON(s0, k_g2_subgroup, nblk(2 * n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, (const int32_t*)d_st_sig, n, (int32_t*)ctx->ok.p);
@@ -811,29 +818,31 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
         sp = span_begin(ctx, ST_G1_MUL, s1);
         LAUNCH_ON(s1, k_g1_mul_u64_pp, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j.p, d_scalars, n, p);
         span_end(ctx, sp, s1);
-        // 5. S = sum_j [c_j] sig_j (M/src/aggregates.rs:303)
-        sp = span_begin(ctx, ST_G2_MUL_SUM, sm);
+        // 5. S = sum_j [c_j] sig_j (M/src/aggregates.rs:303), on aux3: the context's own (highest-priority) stream is left to the
+        //    end of the call
+        sp = span_begin(ctx, ST_G2_MUL_SUM, s3);
         if (n >= B3_MSM_MIN_SETS) {           // bucket method: 8 window sums, each its own pair against -[2^(8w)] G1
-            const size_t nb = (size_t)B3_MSM_WINDOWS * B3_MSM_BUCKETS;
-            CKR(ensure(ctx, ctx->g2j, sizeof(g2_jac) * nb * B3_MSM_SEGS));
+            const unsigned segs = msm_segs(n);
+            const size_t np = msm_parts(segs);
+            CKR(ensure(ctx, ctx->g2j, sizeof(g2_jac) * np));
             CKR(ensure(ctx, ctx->g2j2, sizeof(g2_jac) * B3_MSM_WINDOWS * 256));
-            LAUNCH_ON(sm, k_msm_bucket, nblk(2 * nb * B3_MSM_SEGS), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, d_scalars, n, (g2_jac*)ctx->g2j.p);
-            LAUNCH_ON(sm, k_msm_scale, nblk(2 * B3_MSM_WINDOWS * 256), B3_TPB, (const g2_jac*)ctx->g2j.p, (g2_jac*)ctx->g2j2.p);
-            LAUNCH_ON(sm, k_msm_window_sum, B3_MSM_WINDOWS, 512, (g2_jac*)ctx->g2j2.p);
-            LAUNCH_ON(sm, k_msm_pairs, 1, 32, (const g2_jac*)ctx->g2j2.p, q + n, p + n);
+            LAUNCH_ON(s3, k_msm_bucket, nblk(2 * np), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, d_scalars, n, (g2_jac*)ctx->g2j.p, segs);
+            LAUNCH_ON(s3, k_msm_scale, nblk(2 * B3_MSM_WINDOWS * 256), B3_TPB, (const g2_jac*)ctx->g2j.p, (g2_jac*)ctx->g2j2.p, segs);
+            LAUNCH_ON(s3, k_msm_window_sum, B3_MSM_WINDOWS, 512, (g2_jac*)ctx->g2j2.p);
+            LAUNCH_ON(s3, k_msm_pairs, 1, 32, (const g2_jac*)ctx->g2j2.p, q + n, p + n);
         } else {
             g2_jac* s;
             CKR(ensure(ctx, ctx->g2j, sizeof(g2_jac) * (n + 1)));
-            LAUNCH_ON(sm, k_g2_mul_u64, nblk(2 * n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, d_scalars, n, (g2_jac*)ctx->g2j.p);
-            CKR(g2_sum(ctx, (g2_jac*)ctx->g2j.p, (g2_jac*)ctx->g2j2.p, n, &s));
-            CK(cudaMemcpyAsync(q + n, s, sizeof(g2_jac), cudaMemcpyDeviceToDevice, sm));
-            LAUNCH_ON(sm, k_set_neg_g1_pp, 1, 1, p + n);
+            LAUNCH_ON(s3, k_g2_mul_u64, nblk(2 * n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, d_scalars, n, (g2_jac*)ctx->g2j.p);
+            CKR(g2_sum(ctx, (g2_jac*)ctx->g2j.p, (g2_jac*)ctx->g2j2.p, n, &s, s3));
+            CK(cudaMemcpyAsync(q + n, s, sizeof(g2_jac), cudaMemcpyDeviceToDevice, s3));
+            LAUNCH_ON(s3, k_set_neg_g1_pp, 1, 1, p + n);
         }
-        span_end(ctx, sp, sm);
-        CKR(miller_lines(ctx, sm, q, n_total, n, n_total - n));       // ... and the window sums / S
+        span_end(ctx, sp, s3);
+        CKR(miller_lines(ctx, s3, q, n_total, n, n_total - n));       // ... and the window sums / S
         if (!ctx->serial) {
-            cudaStream_t auxs[3] = {s0, s1, s2};
-            for (int k = 0; k < 3; k++) {
+            cudaStream_t auxs[4] = {s0, s1, s2, s3};
+            for (int k = 0; k < 4; k++) {
                 CK(cudaEventRecord(ctx->ev_join[k], auxs[k]));
                 CK(cudaStreamWaitEvent(sm, ctx->ev_join[k], 0));
             }

@@ -351,28 +351,45 @@ __global__ void __launch_bounds__(B3_TPB) k_g2_mul_u256(const uint8_t* __restric
 // generator (G1_POW256_*).  The GT value is identical.
 #define B3_MSM_WINDOWS 8
 #define B3_MSM_BUCKETS 255
-#define B3_MSM_SEGS 4
-#define B3_MSM_LIST 24
-__global__ void B3_LBH k_msm_bucket(const g2_aff* __restrict__ sigs, const uint64_t* __restrict__ k, size_t n, g2_jac* parts) {
+#define B3_MSM_LIST 48
+// Segments per (window, bucket): the scalars are cut in `segs` contiguous ranges (2 * segs for the TOP window: the
+// reference's scalars are below 2^63, M/src/aggregates.rs:278-287, so its 127 non-empty buckets carry twice the load of
+// the others), one lane pair per (window, bucket, segment); segs grows with the batch so that a lane pair adds ~8 points.
+__host__ __device__ __forceinline__ unsigned msm_segs(size_t n) { return n <= 8192 ? 4u : 8u; }
+__host__ __device__ __forceinline__ size_t msm_parts(unsigned segs) { return (size_t)B3_MSM_BUCKETS * segs * (B3_MSM_WINDOWS + 1); }
+// (window, bucket index 0..254) -> first part and number of parts
+B3_FN size_t msm_part_base(unsigned w, unsigned bi, unsigned segs, unsigned& nseg) {
+    const bool top = w == B3_MSM_WINDOWS - 1;
+    nseg = top ? 2 * segs : segs;
+    return (size_t)w * B3_MSM_BUCKETS * segs + (size_t)bi * nseg;
+}
+__global__ void B3_LBH k_msm_bucket(const g2_aff* __restrict__ sigs, const uint64_t* __restrict__ k, size_t n, g2_jac* parts, unsigned segs) {
     const size_t id = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
-    if (id >= (size_t)B3_MSM_WINDOWS * B3_MSM_BUCKETS * B3_MSM_SEGS) return;
-    const unsigned seg = (unsigned)(id % B3_MSM_SEGS);
-    const unsigned wb = (unsigned)(id / B3_MSM_SEGS);
-    const unsigned w = wb / B3_MSM_BUCKETS, b = wb % B3_MSM_BUCKETS + 1;
-    const size_t per = (n + B3_MSM_SEGS - 1) / B3_MSM_SEGS;
-    size_t j0 = seg * per, j1 = j0 + per;
+    const bool live = id < msm_parts(segs);
+    const size_t blk = (size_t)B3_MSM_BUCKETS * segs;
+    unsigned w = (unsigned)(id / blk);
+    if (w > B3_MSM_WINDOWS - 1) w = B3_MSM_WINDOWS - 1;
+    const unsigned nseg = w == B3_MSM_WINDOWS - 1 ? 2 * segs : segs;
+    const size_t r = id - (size_t)w * blk;
+    const unsigned b = (unsigned)(r / nseg) + 1, seg = (unsigned)(r % nseg);
+    const size_t per = (n + nseg - 1) / nseg;
+    size_t j = seg * per, j1 = j + per;
     if (j1 > n) j1 = n;
+    if (!live || j > n) j = j1 = 0;
     g2h_jac acc;
     pt_set_inf(acc);
-    // Scan first, add afterwards: the matching indices are collected in a small list so that all lane pairs of a warp
-    // run their point additions together (adding inside the scan would serialise the warp: every pair matches at
-    // different positions).
+    // Scan first, add afterwards: the matching indices are collected in a list so that all lane pairs of a warp run
+    // their point additions together (adding inside the scan would serialise the warp: every pair matches at different
+    // positions).  The decisions to flush the lists and to stop are taken by the whole warp.
     uint32_t list[B3_MSM_LIST];
     int cnt = 0;
-    for (size_t j = j0; j <= j1; j++) {
-        const bool last = j == j1;
-        if (!last && (unsigned)((k[j] >> (8 * w)) & 255u) == b) list[cnt++] = (uint32_t)j;
-        if (cnt == B3_MSM_LIST || last) {
+    for (;;) {
+        if (j < j1) {
+            if ((unsigned)((k[j] >> (8 * w)) & 255u) == b) list[cnt++] = (uint32_t)j;
+            j++;
+        }
+        const bool more = __any_sync(0xffffffffu, j < j1);
+        if (!more || __any_sync(0xffffffffu, cnt == B3_MSM_LIST)) {
             for (int t = 0; t < cnt; t++) {
                 g2h_aff p;
                 g2h_load(p, sigs[list[t]]);
@@ -380,11 +397,12 @@ __global__ void B3_LBH k_msm_bucket(const g2_aff* __restrict__ sigs, const uint6
             }
             cnt = 0;
         }
+        if (!more) break;
     }
-    g2h_store(parts[id], acc);
+    if (live) g2h_store(parts[id], acc);
 }
 // out[w * 256 + (b - 1)] = [b] * sum_seg parts;  out[w * 256 + 255] = infinity (padding for the window tree)
-__global__ void B3_LBH k_msm_scale(const g2_jac* parts, g2_jac* out) {
+__global__ void B3_LBH k_msm_scale(const g2_jac* parts, g2_jac* out, unsigned segs) {
     const size_t id = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     if (id >= (size_t)B3_MSM_WINDOWS * 256) return;
     const unsigned w = (unsigned)(id >> 8), bi = (unsigned)(id & 255);
@@ -392,10 +410,11 @@ __global__ void B3_LBH k_msm_scale(const g2_jac* parts, g2_jac* out) {
     if (bi == B3_MSM_BUCKETS) {
         pt_set_inf(t);
     } else {
-        const size_t wb = (size_t)w * B3_MSM_BUCKETS + bi;
-        g2h_load(acc, parts[wb * B3_MSM_SEGS]);
-        for (int sgm = 1; sgm < B3_MSM_SEGS; sgm++) {
-            g2h_load(t, parts[wb * B3_MSM_SEGS + sgm]);
+        unsigned nseg;
+        const size_t base = msm_part_base(w, bi, segs, nseg);
+        g2h_load(acc, parts[base]);
+        for (unsigned sgm = 1; sgm < nseg; sgm++) {
+            g2h_load(t, parts[base + sgm]);
             pt_add(acc, acc, t);
         }
         pt_mul_u64(t, acc, (uint64_t)(bi + 1));
