@@ -302,62 +302,82 @@ def _bench_lanes(eng, lanes, args, world, rank, local_rank, dev):
     def run_steps(steps, use_lanes, host_inputs, flush_l2):
         """`steps` steps; a step = ONE full verification of a C4-shaped batch ON EVERY LANE (len(use_lanes) concurrent calls, each
         on its own context and host thread), so steps * len(use_lanes) batches in all, batch i on lane i % L.
-        N = 1: the lane thread runs the whole call (device-pointer partial + combine on its own context, or the host-pointer
-        b3_verify_multiple).  N > 1: lane threads produce the per-rank partial Miller products; this thread consumes them IN
-        BATCH ORDER (so the collectives are issued in the same order on every rank): all-gather, product, final exponentiation,
-        accept bit."""
+        The lane thread runs the whole call: its partial Miller product (device-pointer entry, or the host-pointer entry with the
+        H2D copies inside), then product + final exponentiation + accept bit on its own context.  N > 1: between the two, this
+        thread issues ONE all-gather per step for the L partials of the step (in step order on every rank) and hands the gathered buffer back to the lane, which finishes batch i after issuing its batch i + L."""
         L = len(use_lanes)
         B = steps * L
         partials = torch.zeros(max(B, 1), PB, dtype=torch.uint8, device=dev)
         torch.cuda.current_stream().synchronize()
         ready = [threading.Event() for _ in range(B)]
+        gathered_ev = [threading.Event() for _ in range(B)]
+        gathered = [None] * B
         results = [None] * B
         errors = []
         full_call = host_inputs and world == 1             # the reference-facing call: b3_verify_multiple on host pointers
 
         def lane_main(t):
             ln = use_lanes[t]
+            pending = None
+
+            def finish(i):
+                gathered_ev[i].wait()
+                if errors:
+                    raise errors[0]
+                results[i] = ln.eng.combine_partials_dev(gathered[i].data_ptr(), world)
+                add_stages(ln.eng)
+
             try:
                 with torch.cuda.stream(ln.stream):
                     for i in range(t, B, L):
                         if flush_l2:
                             flush.fill_(1)                          # evict L2 between iterations (single-lane mode only)
                             ln.stream.synchronize()
+                        p = ln.pin
                         if full_call:
-                            p = ln.pin
                             ok, fb, _gt = ln.eng.verify_multiple(p["sigs"].numpy(), p["pks"].numpy(), p["pk_off"].numpy(), p["msgs"].numpy(),
                                                                  p["msg_off"].numpy(), p["scal"].numpy().view(np.uint64), want_gt=True)
                             results[i] = (ok, fb)
                             add_stages(ln.eng)
+                            continue
+                        if host_inputs:
+                            ln.eng.verify_multiple_partial(p["sigs"].numpy(), p["pks"].numpy(), p["pk_off"].numpy(), p["msgs"].numpy(),
+                                                           p["msg_off"].numpy(), p["scal"].numpy().view(np.uint64), base, partials[i].data_ptr())
                         else:
-                            if host_inputs:
-                                for k in ln.pin:
-                                    ln.d[k].copy_(ln.pin[k], non_blocking=True)
-                                ln.stream.synchronize()
                             ln.partial_dev(n, base, partials[i].data_ptr())
+                        add_stages(ln.eng)
+                        if world == 1:
+                            results[i] = ln.eng.combine_partials_dev(partials[i].data_ptr(), 1)
                             add_stages(ln.eng)
-                            if world == 1:
-                                results[i] = ln.eng.combine_partials_dev(partials[i].data_ptr(), 1)
-                                add_stages(ln.eng)
+                            continue
+                        # N > 1: hand the partial to the gathering thread and finish the PREVIOUS batch of this lane, whose
+                        # all-gather has had a whole batch time to complete (ranks may drift by up to one batch per lane)
                         ready[i].set()
+                        if pending is not None:
+                            finish(pending)
+                        pending = i
+                    if pending is not None:
+                        finish(pending)
             except BaseException as ex:                              # noqa: BLE001
                 errors.append(ex)
-                for ev in ready:
+                for ev in ready + gathered_ev:
                     ev.set()
 
         threads = [threading.Thread(target=lane_main, args=(t,), daemon=True) for t in range(L)]
         for th in threads:
             th.start()
-        for i in range(B):
-            ready[i].wait()
-            if errors:
-                break
-            if world == 1:
-                continue
-            g = sharding.all_gather_partials(partials[i], world)      # the ONLY collective: world x 592 bytes over NCCL
-            torch.cuda.current_stream().synchronize()
-            results[i] = eng.combine_partials_dev(g.data_ptr(), world)
-            add_stages(eng)
+        if world > 1:
+            for k in range(steps):
+                for i in range(k * L, (k + 1) * L):
+                    ready[i].wait()
+                if errors:
+                    break
+                # the ONLY collective: one all-gather per step for the L calls in flight (world x L x 592 bytes over NCCL)
+                g = sharding.all_gather_partial_batch(partials[k * L:(k + 1) * L], world)
+                torch.cuda.current_stream().synchronize()
+                for j in range(L):
+                    gathered[k * L + j] = g[j]
+                    gathered_ev[k * L + j].set()
         for th in threads:
             th.join()
         if errors:

@@ -136,6 +136,11 @@ int b3_verify_batch(b3_ctx*, int mode, const uint8_t* sigs192, const uint8_t* pk
 int b3_verify_multiple_partial_dev(b3_ctx*, const uint8_t* sigs192_dev, const uint8_t* pks96_dev,
                                    const uint32_t* pk_off_dev, const uint8_t* msgs_dev, const uint32_t* msg_off_dev,
                                    const uint64_t* scalars_dev, size_t n, int64_t index_base, uint8_t* partial_dev);
+/* the same with this rank's shard in HOST memory (the sharded form of b3_verify_multiple: M/src/aggregates.rs:261-316 on
+ * sets [index_base, index_base + n)); the partial stays on the device for the all-gather */
+int b3_verify_multiple_partial(b3_ctx*, const uint8_t* sigs192, const uint8_t* pks96, const uint32_t* pk_off,
+                               const uint8_t* msgs, const uint32_t* msg_off, const uint64_t* scalars, size_t n,
+                               int64_t index_base, uint8_t* partial_dev);
 /* product of n_partials partials (gathered from all ranks) -> one final exponentiation -> accept, first_bad, gt */
 int b3_combine_partials_dev(b3_ctx*, const uint8_t* partials_dev, size_t n_partials, int* accept, int64_t* first_bad,
                             uint8_t* gt576);

@@ -66,6 +66,7 @@ def lib():
         "b3_verify_batch": ([vp, ctypes.c_int, u8p, u8p, vp, u8p, vp, sz, i32p, i32p, u8p], ctypes.c_int),
         "b3_verify_batch_dev": ([vp, ctypes.c_int, vp, vp, vp, vp, vp, sz, vp, vp, vp], ctypes.c_int),
         "b3_verify_multiple_partial_dev": ([vp, vp, vp, vp, vp, vp, vp, sz, ctypes.c_int64, vp], ctypes.c_int),
+        "b3_verify_multiple_partial": ([vp, u8p, u8p, vp, u8p, vp, vp, sz, ctypes.c_int64, vp], ctypes.c_int),
         "b3_combine_partials_dev": ([vp, vp, sz, ip, i64p, u8p], ctypes.c_int),
         "b3_hash_to_g2_dev": ([vp, vp, vp, sz, vp], ctypes.c_int),
         "b3_g1_aggregate_dev": ([vp, vp, vp, sz, vp, vp], ctypes.c_int),
@@ -89,6 +90,6 @@ EXPORTED_SYMBOLS = [
     "b3_g1_aggregate", "b3_g2_aggregate", "b3_hash_to_g2", "b3_verify", "b3_fast_aggregate_verify",
     "b3_fast_aggregate_verify_pre_aggregated", "b3_aggregate_verify", "b3_verify_multiple",
     "b3_verify_batch", "b3_verify_batch_dev",
-    "b3_verify_multiple_partial_dev", "b3_combine_partials_dev", "b3_hash_to_g2_dev", "b3_g1_aggregate_dev",
+    "b3_verify_multiple_partial_dev", "b3_verify_multiple_partial", "b3_combine_partials_dev", "b3_hash_to_g2_dev", "b3_g1_aggregate_dev",
     "b3_g1_mul_gen", "b3_g2_mul", "b3_imad_peak",
 ]

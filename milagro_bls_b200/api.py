@@ -279,6 +279,17 @@ class Engine:
         self._ck(self.L.b3_verify_multiple_partial_dev(self.handle, d_sigs, d_pks, d_pk_off, d_msgs, d_msg_off, d_scalars, n,
                                                        index_base, d_partial))
 
+    def verify_multiple_partial(self, sigs192, pks96, pk_offsets, msgs_blob, msg_offsets, scalars, index_base, d_partial):
+        """This rank's shard from HOST buffers -> 592-byte partial in device memory at d_partial (b3_verify_multiple_partial)."""
+        sc = np.ascontiguousarray(scalars, dtype=np.uint64)
+        moff = np.ascontiguousarray(msg_offsets, dtype=np.uint32)
+        ps, k1 = _buf(sigs192)
+        pp, k2 = _buf(pks96)
+        pm, k3 = _buf(msgs_blob)
+        po = None if pk_offsets is None else np.ascontiguousarray(pk_offsets, dtype=np.uint32)
+        self._ck(self.L.b3_verify_multiple_partial(self.handle, ps, pp, None if po is None else po.ctypes.data, pm, moff.ctypes.data,
+                                                   sc.ctypes.data, len(sc), index_base, d_partial))
+
     def combine_partials_dev(self, d_partials, n_partials, want_gt=False):
         ok = ctypes.c_int(0)
         fb = ctypes.c_int64(-1)

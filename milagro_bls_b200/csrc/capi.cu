@@ -948,6 +948,40 @@ extern "C" int b3_verify_multiple_partial_dev(b3_ctx* ctx, const uint8_t* sigs19
     cudaGetLastError();
     return B3_OK;
 }
+// host-pointer form of the sharded call: this rank's shard comes from HOST memory (the keys are copied on the aggregation
+// stream, overlapped with the other stages, as in b3_verify_multiple); the partial stays on the device for the all-gather
+extern "C" int b3_verify_multiple_partial(b3_ctx* ctx, const uint8_t* sigs192, const uint8_t* pks96, const uint32_t* pk_off, const uint8_t* msgs,
+                                          const uint32_t* msg_off, const uint64_t* scalars, size_t n, int64_t index_base, uint8_t* partial_dev) {
+    CKR(begin(ctx));
+    if (!partial_dev) return B3_ERR_ARG;
+    if (n && (!sigs192 || !pks96 || !msg_off || !scalars)) return B3_ERR_ARG;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    mark_reset(ctx);
+    size_t total_keys = pk_off ? pk_off[n] : n;
+    if (n) {
+        CKR(h2d(ctx, ctx->in_a, sigs192, 192 * n));
+        CKR(ensure(ctx, ctx->in_b, 96 * total_keys + 1));             // copied inside the core, on the aggregation stream
+        if (pk_off) CKR(h2d(ctx, ctx->in_e, pk_off, 4 * (n + 1)));
+        CKR(h2d(ctx, ctx->in_c, msgs, msg_off[n]));
+        CKR(h2d(ctx, ctx->in_d, msg_off, 4 * (n + 1)));
+        CKR(h2d(ctx, ctx->in_f, scalars, 8 * n));
+    }
+    fp12* res;
+    long long* d_fb;
+    int perr;
+    CKR(verify_multiple_core(ctx, (const uint8_t*)ctx->in_a.p, (const uint8_t*)ctx->in_b.p, pk_off ? (const uint32_t*)ctx->in_e.p : nullptr,
+                             total_keys, (const uint8_t*)ctx->in_c.p, (const uint32_t*)ctx->in_d.p, (const uint64_t*)ctx->in_f.p, n, index_base,
+                             &res, &d_fb, &perr, pks96));
+    if (perr) return perr;
+    LAUNCH(k_pack_partial, 1, 1, (const fp12*)res, (const long long*)d_fb, (partial_rec*)partial_dev);
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CKR(sync(ctx));
+    mark_collect(ctx);
+    cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev[0], ctx->ev[1]);
+    if (cudaEventElapsedTime(&ctx->last_ms[1], ctx->ev[2], ctx->ev[3]) != cudaSuccess) ctx->last_ms[1] = 0.f;
+    cudaGetLastError();
+    return B3_OK;
+}
 extern "C" int b3_combine_partials_dev(b3_ctx* ctx, const uint8_t* partials_dev, size_t n_partials, int* accept, int64_t* first_bad,
                                        uint8_t* gt576) {
     CKR(begin(ctx));

@@ -35,6 +35,20 @@ def all_gather_partials(partial, world, group=None):
     return out
 
 
+def all_gather_partial_batch(partials, world, group=None):
+    """Several calls in flight per rank: partials = uint8 tensor (L, PARTIAL_BYTES), row j = this rank's partial of call j.
+    ONE all-gather for all L calls -> uint8 tensor (L, world, PARTIAL_BYTES): row j holds the world partials of call j,
+    rank-major, ready for b3_combine_partials_dev."""
+    if partials.dtype != torch.uint8 or partials.dim() != 2 or partials.shape[1] != PARTIAL_BYTES:
+        raise ValueError("partials must be a (L, %d) uint8 tensor" % PARTIAL_BYTES)
+    L = partials.shape[0]
+    if world == 1:
+        return partials.reshape(L, 1, PARTIAL_BYTES).clone()
+    out = torch.empty(world * L * PARTIAL_BYTES, dtype=torch.uint8, device=partials.device)
+    dist.all_gather_into_tensor(out, partials.contiguous().view(-1), group=group)
+    return out.view(world, L, PARTIAL_BYTES).transpose(0, 1).contiguous()
+
+
 def first_bad_of(partials):
     """Minimum of the int64 first-bad words of a gathered partial buffer; -1 if no shard saw a bad signature."""
     t = partials.view(-1, PARTIAL_BYTES)[:, 576:584].contiguous().view(torch.int64).reshape(-1)

@@ -489,6 +489,46 @@ def _batch_items():
     return items
 
 
+def test_verify_multiple_sharded_host_partials(eng):
+    """The sharded form on one GPU: two shards through b3_verify_multiple_partial (host pointers) and
+    b3_verify_multiple_partial_dev, combined by b3_combine_partials_dev, give the GT bytes / accept / global first_bad of
+    the unsharded call -- which the oracle pins."""
+    import torch
+    import milagro_bls_b200 as mb
+    sets_o = _make_sets(5, 3)
+    rng, rng_o = mb.SeededRng(b"shard"), O.SeededRng(b"shard")
+    scalars = np.array([mb.draw_scalar(rng) for _ in sets_o], dtype=np.uint64)
+    msgs = [m for _, _, m in sets_o]
+
+    def shard(lo, hi, sig_override=None):
+        sub = sets_o[lo:hi]
+        sigs = b"".join(g2w(sig_override.get(lo + j, s)) if sig_override else g2w(s) for j, (s, _, _) in enumerate(sub))
+        pks = b"".join(g1w(P) for _, p, _ in sub for P in p)
+        offs = [3 * j for j in range(len(sub) + 1)]
+        moff = np.cumsum([0] + [len(m) for m in msgs[lo:hi]])
+        return sigs, pks, offs, b"".join(msgs[lo:hi]), moff, scalars[lo:hi]
+
+    dev = torch.device("cuda", 0)
+    ok_o, gt_o = O.verify_multiple_aggregate_signatures(
+        rng_o.fill, [(s, O.aggregate_public_keys(p), m) for s, p, m in sets_o], want_gt=True)
+    for bad in (None, {3: O.map_to_curve_g2((5, 7))}):
+        parts = torch.zeros(2, mb._lib.PARTIAL_BYTES, dtype=torch.uint8, device=dev)
+        a = shard(0, 2, bad)
+        eng.verify_multiple_partial(*a, 0, parts[0].data_ptr())
+        b = shard(2, 5, bad)
+        d = [torch.from_numpy(np.frombuffer(x, dtype=np.uint8).copy() if isinstance(x, bytes) else np.ascontiguousarray(x)).to(dev)
+             for x in (b[0], b[1], np.array(b[2], dtype=np.uint32).view(np.int32), b[3], np.array(b[4], dtype=np.uint32).view(np.int32),
+                       b[5].view(np.int64))]
+        eng.verify_multiple_partial_dev(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), d[4].data_ptr(),
+                                        d[5].data_ptr(), 3, 2, parts[1].data_ptr())
+        torch.cuda.synchronize()
+        ok, fb, gt = eng.combine_partials_dev(parts.data_ptr(), 2, want_gt=True)
+        if bad is None:
+            assert ok and ok_o and fb == -1 and gt == O.f12_to_bytes(gt_o)
+        else:
+            assert not ok and fb == 3                                   # global index of the non-subgroup signature
+
+
 @pytest.fixture(params=[1, 2], ids=["cta_per_item", "thread_per_item"])
 def item_kernel(eng, request):
     """Both finishing kernels of b3_verify_batch on the same small batches (the default picks by batch size)."""

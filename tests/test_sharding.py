@@ -73,6 +73,14 @@ def _worker(rank, world, port, n, bad_at, out_q):
             rec = raw[r * sharding.PARTIAL_BYTES:(r + 1) * sharding.PARTIAL_BYTES]
             f = O.f12_mul(f, _f12_from_bytes(rec[:576]))
         gt = O.f12_to_bytes(O.fexp(f))
+        # several calls in flight: one all-gather for L = 3 calls; row j = the world partials of call j, rank-major
+        tag = lambda r, j: bytes([16 * r + j]) * sharding.PARTIAL_BYTES
+        mine = torch.frombuffer(bytearray(b"".join(tag(rank, j) for j in range(3))), dtype=torch.uint8).view(3, -1)
+        both = sharding.all_gather_partial_batch(mine, world)
+        assert tuple(both.shape) == (3, world, sharding.PARTIAL_BYTES) and both.is_contiguous()
+        for j in range(3):
+            for r in range(world):
+                assert bytes(both[j, r].numpy().tobytes()) == tag(r, j)
         out_q.put((rank, sharding.first_bad_of(gathered), gt))
     finally:
         dist.destroy_process_group()
