@@ -48,6 +48,9 @@ FP_MULS_PER_SET = 16400
 # what this implementation actually executes per set (inversion-free maps, bucket-method sum, split
 # Miller loop), in the same unit -- reported beside the SURVEY figure so the fraction cannot flatter the kernels
 EXEC_FP_MULS_PER_SET = 13400
+# DRAM bytes (read + write) per launch at the C4 shape from the committed `ncu --set full` captures (profiles/r1q_*_full.txt)
+NCU_TRAFFIC_BYTES = {"hash_to_g2_affine": 550400 + 6861312, "miller_accumulate": 162113792 + 4973056}
+CPU_PASSES = 4                # timed passes of the CPU baseline over its 2048-set sample (~10 s of CPU work per 4 cores)
 B3_EXTRA_PAIRS = 8            # window sums of the bucket-method signature sum, each its own pair
 BYTES_PER_SET = KEYS_PER_SET * 96 + 192 + MSG_LEN + 8          # algorithmic HBM bytes read per set
 
@@ -186,6 +189,7 @@ def main():
     ap.add_argument("--inflight", type=int, default=6,
                     help="verification batches in flight per GPU (one b3_ctx + host thread each; 1 = one call at a time)")
     ap.add_argument("--h2c-msgs", type=int, default=65536, help="messages per hash_to_G2 batch of the second metric")
+    ap.add_argument("--no-next-rows", action="store_true", help="skip the SURVEY 8(f) rows (decompression, aggregation, per-item verification)")
     ap.add_argument("--breakdown", action="store_true", help="print the per-stage device times to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -272,6 +276,67 @@ def _bench(eng, args, world, rank, local_rank, dev):
         torch.cuda.synchronize()
         for ln in lanes:
             ln.close()
+
+
+def _bench_next_rows(eng, lane, dev, n, nk):
+    """SURVEY.md 8(f): batched decompression + validation (PublicKey::from_bytes / Signature::from_bytes), signature aggregation,
+    per-item verification.  Host-pointer calls are timed by wall clock around the synchronous C-ABI call (H2D/D2H inside);
+    the per-item verification runs on the lane's device-resident C4 batch and is timed by the library's CUDA events.
+    Each row carries a size-independent parity property checked here (round trip / all items accept); bit-exact parity with
+    the oracle is in tests/test_gpu_parity.py."""
+    import numpy as np
+    import torch
+    from milagro_bls_b200 import _lib
+    peak = eng.imad_peak(wide=True)
+    out = {}
+
+    def wall(fn, reps=3):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = fn()
+        return (time.perf_counter() - t0) / reps, r
+
+    def row(name, units, secs, fp_muls, extra=None):
+        d = {"value": units / secs, "unit": name.split(":")[1], "units_per_call": units, "ms_per_call": secs * 1e3,
+             "algorithmic_fp_muls_per_unit": fp_muls, "imad_frac": units / secs * fp_muls * MACS_PER_FP_MUL / peak}
+        d.update(extra or {})
+        out[name.split(":")[0]] = d
+
+    keys96 = lane.pin["pks"].numpy()[:96 * 65536]
+    nkeys = len(keys96) // 96
+    c48, st = eng.g1_compress(keys96)
+    assert not st.any()
+    secs, (back, st) = wall(lambda: eng.g1_decompress(c48, validate=True))
+    assert not st.any() and back.tobytes() == keys96.tobytes(), "G1 compress -> decompress round trip"
+    row("g1_decompress_validate:keys/s", nkeys, secs, 490 + 1000, {"timing": "wall clock, host pointers (48 B in, 96 B + status out per key)"})
+    sig192 = lane.pin["sigs"].numpy()
+    nsig = len(sig192) // 192
+    c96, st = eng.g2_compress(sig192)
+    assert not st.any()
+    secs, (back, st) = wall(lambda: eng.g2_decompress(c96))
+    assert not st.any() and back.tobytes() == sig192.tobytes(), "G2 compress -> decompress round trip"
+    row("g2_decompress:signatures/s", nsig, secs, 1100, {"timing": "wall clock, host pointers (96 B in, 192 B + status out per signature)"})
+    off = np.arange(0, nsig + 1, 4, dtype=np.uint32)
+    secs, (agg, st) = wall(lambda: eng.g2_aggregate(sig192, off))
+    assert not st.any()
+    row("g2_aggregate:signatures/s", nsig, secs, 30, {"signatures_per_aggregate": 4, "timing": "wall clock, host pointers"})
+    # per-item verification (fast_aggregate_verify of every set of the resident batch: nk keys per item, one final exponentiation each)
+    d = lane.d
+    acc = torch.zeros(n, dtype=torch.int32, device=dev)
+    stt = torch.zeros(n, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    best = None
+    for _ in range(3):
+        lane.eng.verify_batch_dev(_lib.ITEM_FAST_AGGREGATE, d["sigs"].data_ptr(), d["pks"].data_ptr(), d["pk_off"].data_ptr(),
+                                  d["msgs"].data_ptr(), d["msg_off"].data_ptr(), n, acc.data_ptr(), stt.data_ptr())
+        ms = lane.eng.last_kernel_ms(0)
+        best = ms if best is None else min(best, ms)
+    torch.cuda.synchronize()
+    assert int(acc.sum()) == n and not bool(stt.any()), "every set of the valid batch verifies on its own"
+    row("verify_batch_fast_aggregate:items/s", n, best * 1e-3, 1400 + 6700 + 1170 + 12260 + 8000,
+        {"keys_per_item": nk, "timing": "CUDA events of the call, inputs resident in HBM; best of 3"})
+    return out
 
 
 def _bench_lanes(eng, lanes, args, world, rank, local_rank, dev):
@@ -467,6 +532,9 @@ def _bench_lanes(eng, lanes, args, world, rank, local_rank, dev):
     ms_h2c = float(t.item())
     h2c_rate = nh * world * args.steps / (ms_h2c * 1e-3)
 
+    # rows SURVEY.md 8(f) marks "next" (the callers / data formats either side of the path), measured on rank 0 at N = 1
+    next_rows = _bench_next_rows(eng, lanes[0], dev, n, nk) if (world == 1 and not args.no_next_rows) else None
+
     total_sets = n * world                               # per call across the ranks
     value = total_sets * S * args.steps / (ms_res * 1e-3)
     e2e = total_sets * S * args.steps / (ms_e2e * 1e-3)
@@ -499,7 +567,10 @@ def _bench_lanes(eng, lanes, args, world, rank, local_rank, dev):
             hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
         hbm_achieved = BYTES_PER_SET * n / (step_ms * 1e-3) / 1e9
         roofline = {"bound": "imad", "kernel": dom, "achieved": achieved / 1e9, "peak": peak_mac / 1e9, "unit": "GMAC/s (32x32->64 multiply-accumulate)",
-                    "frac": achieved / peak_mac, "traffic": None,
+                    "frac": achieved / peak_mac,
+                    "traffic": NCU_TRAFFIC_BYTES.get(dom) if (n == SETS_PER_GPU and nk == KEYS_PER_SET) else None,
+                    "traffic_note": "DRAM bytes read + written per launch, ncu --set full capture (profiles/r1q_h2c_full.txt); the kernel is "
+                                    "bound by the integer multiply pipe, not HBM",
                     "kernel_ms": dom_ms, "algorithmic_fp_muls_per_unit": FP_MULS[dom], "macs_per_fp_mul": MACS_PER_FP_MUL, "units_per_launch": units,
                     "peak_source": "live probe b3_imad_peak(wide=1): IMAD.WIDE carry chains, all SMs",
                     "plain_imad_peak_gops": peak_imad / 1e9,
@@ -521,9 +592,12 @@ def _bench_lanes(eng, lanes, args, world, rank, local_rank, dev):
         if not args.no_cpu_baseline and world == 1:
             try:
                 cpu_reference_run(max(os.cpu_count() or 1, args.ref_sets), nk, 0xB200, os.cpu_count() or 1)      # warm-up pass
-                c = cpu_reference_run(max(os.cpu_count() or 1, args.ref_sets), nk, 0xB200, os.cpu_count() or 1)
-                cpu = {"value": c["sets"] / c["seconds"], "unit": "sets/s", "cores": c["threads"], "kind": c["kind"],
-                       "sample": f"{c['sets']} sets x {nk} keys, {c['threads']} independent single-threaded instances, {c['seconds']:.1f} s"}
+                passes = [cpu_reference_run(max(os.cpu_count() or 1, args.ref_sets), nk, 0xB200, os.cpu_count() or 1) for _ in range(CPU_PASSES)]
+                c = passes[-1]
+                c_sets, c_sec = sum(x["sets"] for x in passes), sum(x["seconds"] for x in passes)
+                cpu = {"value": c_sets / c_sec, "unit": "sets/s", "cores": c["threads"], "kind": c["kind"],
+                       "sample": f"{CPU_PASSES} passes over {c['sets']} sets x {nk} keys, {c['threads']} independent single-threaded instances, "
+                                 f"{c_sec:.1f} s wall = {c_sec * c['threads']:.0f} core-seconds"}
             except Exception as ex:                                        # noqa: BLE001
                 cpu = {"value": None, "unit": "sets/s", "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
         cache = (f"{S} batches in flight on {S} contexts, each with its own {h2d_bytes / 1e6:.0f} MB of inputs ({S * h2d_bytes / 1e6:.0f} MB > 126 MB L2) "
@@ -547,6 +621,7 @@ def _bench_lanes(eng, lanes, args, world, rank, local_rank, dev):
                "hash_to_g2": {"value": h2c_rate, "unit": "hash_to_G2/s", "messages_per_gpu": nh, "message_bytes": MSG_LEN,
                               "ms_per_batch": ms_h2c / args.steps,
                               "imad_frac": h2c_rate / world * FP_MULS["hash_to_g2_affine"] * MACS_PER_FP_MUL / peak_mac},
+               "next_rows": next_rows,
                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                "accept": bool(last[0])}
         if args.breakdown:
