@@ -236,6 +236,40 @@ B3_FN_NOINLINE void pt_mul_u64(jac<F>& r, const jac<F>& p, uint64_t k) {
     }
     r = acc;
 }
+// [k]P, k a 64-bit scalar, SIGNED 4-BIT FIXED WINDOWS: k = sum_i d_i 16^i + c 16^16 with d_i in [-8, 7] (the nibbles of
+// k + 0x88..8 minus 8, c = the carry out of bit 64).  Every thread of a warp adds at the same steps -- with one thread per
+// set and a different scalar in every lane, double-and-add runs its additions at half the lanes (each bit is set in
+// about half of them) -- and the work drops from 63 doublings + ~32 additions to a table of [1..8]P (4 doublings +
+// 3 additions), 64 doublings and <= 17 additions.  pt_add is complete (infinity, doubling, inverse operands), so the
+// result is [k]P for ANY point of the curve, also outside the prime-order subgroup.
+template <class F>
+B3_FN_NOINLINE void pt_mul_u64_w4(jac<F>& r, const jac<F>& p, uint64_t k) {
+    jac<F> tbl[8];                                  // tbl[j] = [j + 1] P
+    tbl[0] = p;
+    pt_dbl(tbl[1], p);
+    pt_add(tbl[2], tbl[1], p);
+    pt_dbl(tbl[3], tbl[1]);
+    pt_add(tbl[4], tbl[3], p);
+    pt_dbl(tbl[5], tbl[2]);
+    pt_add(tbl[6], tbl[5], p);
+    pt_dbl(tbl[7], tbl[3]);
+    const uint64_t off = 0x8888888888888888ull;
+    const uint64_t ks = k + off;
+    const int carry = ks < k ? 1 : 0;
+    jac<F> acc;
+    pt_set_inf(acc);
+    if (carry) acc = p;
+    for (int i = 15; i >= 0; i--) {
+        pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc);
+        const int d = (int)((ks >> (4 * i)) & 15u) - 8;
+        if (d != 0) {
+            jac<F> q = tbl[(d < 0 ? -d : d) - 1];
+            if (d < 0) pt_neg(q, q);
+            pt_add(acc, acc, q);
+        }
+    }
+    r = acc;
+}
 // [k]P for affine P (mixed additions)
 template <class F>
 B3_FN_NOINLINE void pt_mul_u64_aff(jac<F>& r, const aff<F>& p, uint64_t k) {

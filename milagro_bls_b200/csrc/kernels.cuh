@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(B3_TPB) k_g1_mul_u64_pp(const g1_jac* in, cons
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g1_jac p = in[i], r;
-    pt_mul_u64(r, p, k[i]);
+    pt_mul_u64_w4(r, p, k[i]);
     g1_pp o;
     g1_pp_from_jac(o, r);
     out[i] = o;

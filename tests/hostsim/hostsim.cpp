@@ -195,6 +195,7 @@ int hs_g1_op(int op, const uint8_t* a96, const uint8_t* b96, uint64_t k, uint8_t
         case 1: pt_mul_u64(R, P, k); break;
         case 2: pt_dbl(R, P); break;
         case 3: pt_add_aff(R, P, B); break;
+        case 5: pt_mul_u64_w4(R, P, k); break;
         default: g1_phi(R, P); break;
     }
     g1_aff o; pt_to_aff(o, R);

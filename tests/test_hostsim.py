@@ -199,6 +199,19 @@ def test_g1_ops(hs):
     for k in [0, 1, 2, 0xd201000000010000, (1 << 64) - 1, 0x7fffffffffffffff]:
         hs.hs_g1_op(1, g1w(A), g1w(None), k, out)
         assert out.raw == g1w(O.g1_mul(A, k))
+    # signed fixed-window multiplication ([c] apk of verify_multiple): digit edge cases (all -8, all 7, carry out of bit 64,
+    # zero digits), a point of small order outside G1 (pt_add must take its doubling / inverse branches) and infinity
+    ks = [0, 1, 7, 8, 9, 15, 16, 0x8888888888888888, 0x7777777777777777, 0xffffffffffffffff, 0x8000000000000000,
+          0x7fffffffffffffff, 0x1000000000000000, 0x00f0000000000f00, 0xd201000000010000, 0x123456789abcdef0]
+    for k in ks:
+        hs.hs_g1_op(5, g1w(A), g1w(None), k, out)
+        assert out.raw == g1w(O.g1_mul(A, k)), hex(k)
+    T3 = (0, 2)                                   # (0, 2) is on y^2 = x^3 + 4 and has order 3
+    assert O.g1_add(O.g1_add(T3, T3), T3) is None
+    for k in ks:
+        hs.hs_g1_op(5, g1w(T3), g1w(None), k, out)
+        assert out.raw == g1w([None, T3, O.g1_add(T3, T3)][k % 3]), hex(k)
+    hs.hs_g1_op(5, g1w(None), g1w(None), 12345, out); assert out.raw == g1w(None)
     hs.hs_g1_op(2, g1w(A), g1w(None), 0, out); assert out.raw == g1w(O.g1_add(A, A))
     hs.hs_g1_op(4, g1w(A), g1w(None), 0, out); assert out.raw == g1w(O.g1_mul(A, (-O.BNX * O.BNX) % O.r))
     oc, sg = ctypes.c_int(), ctypes.c_int()
