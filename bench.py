@@ -7,7 +7,7 @@ Contract (see the task statement):  python bench.py --gpus N --steps K --warmup 
     is BASELINE.json configs[4] (2^16 sets, NCCL combine of the 592-byte partial Miller products).
   * one call = one full verification of a C4 batch: G2 subgroup checks, G1 key aggregation, [c]apk, hash_to_G2,
     [c]sig sum, n+8 Miller loops, Fp12 product, (all-gather,) one final exponentiation, accept bit.
-  * a step = one such call on EACH of --inflight (default 6) contexts per GPU, running concurrently: one b3_ctx + one
+  * a step = one such call on EACH of --inflight (default 8) contexts per GPU, running concurrently: one b3_ctx + one
     host thread per call, the reference's own threading model (re-entrant types, callers parallelise externally).  A
     single 8192-set call is a chain of latency-bound kernels (~7 ms end to end) that cannot fill 148 SMs by itself;
     K steps = K x inflight full verifications of 8192 sets each.
@@ -186,7 +186,7 @@ def main():
     ap.add_argument("--ref-sets", type=int, default=2048,
                     help="sets per step of the CPU reference arm / cpu_baseline sample (~20 s of CPU work on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=6,
+    ap.add_argument("--inflight", type=int, default=8,
                     help="verification batches in flight per GPU (one b3_ctx + host thread each; 1 = one call at a time)")
     ap.add_argument("--h2c-msgs", type=int, default=65536, help="messages per hash_to_G2 batch of the second metric")
     ap.add_argument("--no-next-rows", action="store_true", help="skip the SURVEY 8(f) rows (decompression, aggregation, per-item verification)")

@@ -18,6 +18,8 @@ static const uint8_t kDstG2[] = "BLS_SIG_BLS12381G2_XMD:SHA-256_SSWU_RO_POP_";  
 static const size_t kDstG2Len = 43;
 
 #define B3_MAX_MARKS 24
+// sets from which the key aggregation uses 4 lanes per set instead of 8 (less shuffle-tree overhead, twice the latency)
+static const size_t kAggG4Min = getenv("B3_AGG_G4_MIN") ? (size_t)atol(getenv("B3_AGG_G4_MIN")) : 4096;
 #define B3_MSM_MIN_SETS 512     // below this, S = sum [c_j] sig_j uses n separate ladders + a tree
 #define B3_N_STAGES 11
 // stage ids (b3_ctx_stage_ms / b3_stage_name)
@@ -660,7 +662,7 @@ static int verify_batch_core(b3_ctx* ctx, int mode, const uint8_t* d_sigs, const
     sp = span_begin(ctx, ST_AGGREGATE, s1);
     if (mode == B3_ITEM_FAST_AGGREGATE) {
         size_t avg = total_keys / n;
-        if (n >= 16384 || avg <= 8) LAUNCH_ON(s1, k_g1_aggregate<4>, nblk(n * 4), B3_TPB, d_pks, d_pk_off, n, (g1_jac*)ctx->g1j.p, d_st_key);
+        if (n >= kAggG4Min || avg <= 8) LAUNCH_ON(s1, k_g1_aggregate<4>, nblk(n * 4), B3_TPB, d_pks, d_pk_off, n, (g1_jac*)ctx->g1j.p, d_st_key);
         else if (n >= 2048 || avg <= 32) LAUNCH_ON(s1, k_g1_aggregate<8>, nblk(n * 8), B3_TPB, d_pks, d_pk_off, n, (g1_jac*)ctx->g1j.p, d_st_key);
         else LAUNCH_ON(s1, k_g1_aggregate<32>, nblk(n * 32), B3_TPB, d_pks, d_pk_off, n, (g1_jac*)ctx->g1j.p, d_st_key);
     } else {
@@ -808,7 +810,7 @@ static int verify_multiple_core(b3_ctx* ctx, const uint8_t* d_sigs, const uint8_
         sp = span_begin(ctx, ST_AGGREGATE, s1);
         if (d_pk_off) {
             size_t avg = total_keys / n;
-            if (n >= 16384 || avg <= 8) LAUNCH_ON(s1, k_g1_aggregate<4>, nblk(n * 4), B3_TPB, d_pks, d_pk_off, n, (g1_jac*)ctx->g1j.p, d_st_key);
+            if (n >= kAggG4Min || avg <= 8) LAUNCH_ON(s1, k_g1_aggregate<4>, nblk(n * 4), B3_TPB, d_pks, d_pk_off, n, (g1_jac*)ctx->g1j.p, d_st_key);
             else if (n >= 2048 || avg <= 32) LAUNCH_ON(s1, k_g1_aggregate<8>, nblk(n * 8), B3_TPB, d_pks, d_pk_off, n, (g1_jac*)ctx->g1j.p, d_st_key);
             else LAUNCH_ON(s1, k_g1_aggregate<32>, nblk(n * 32), B3_TPB, d_pks, d_pk_off, n, (g1_jac*)ctx->g1j.p, d_st_key);
         } else {

@@ -489,6 +489,32 @@ def _batch_items():
     return items
 
 
+def test_verify_multiple_full_size_properties(eng):
+    """More than a C4 batch (8200 sets: the 8-segment bucket-method path, four-lane key aggregation, 14 accumulation
+    chunks), checked through size-independent properties: a valid batch accepts with GT = one; because the final
+    exponentiation is a homomorphism and every valid set contributes one, the GT of the batch with ONE tampered set equals
+    the GT of that set verified alone with the same scalar -- which the Python oracle pins."""
+    rnd = random.Random(99)
+    n, bad = 8200, 6001
+    sks = [rnd.randrange(1, O.r) for _ in range(n)]
+    pk = eng.g1_mul_gen(sks)
+    msgs = [rnd.getrandbits(256).to_bytes(32, "big") for _ in range(n)]
+    sig = eng.g2_mul(eng.hash_to_g2(msgs).reshape(-1), sks)
+    scalars = np.array([rnd.randrange(1, 1 << 63) for _ in range(n)], dtype=np.uint64)
+    moff = list(range(0, 32 * n + 1, 32))
+    ok, fb, gt = eng.verify_multiple(sig.reshape(-1), pk.reshape(-1), None, b"".join(msgs), moff, scalars, want_gt=True)
+    assert ok and fb == -1 and gt == O.f12_to_bytes(O.F12_ONE)
+    tampered = list(msgs); tampered[bad] = b"tampered" + msgs[bad][8:]
+    ok, fb, gt = eng.verify_multiple(sig.reshape(-1), pk.reshape(-1), None, b"".join(tampered), moff, scalars, want_gt=True)
+    ok1, fb1, gt1 = eng.verify_multiple(sig[bad].tobytes(), pk[bad].tobytes(), None, tampered[bad], [0, 32], scalars[bad:bad + 1], want_gt=True)
+    assert not ok and fb == -1 and not ok1 and gt == gt1 and gt != O.f12_to_bytes(O.F12_ONE)
+    c = int(scalars[bad])
+    ok_o, gt_o = O.verify_multiple_aggregate_signatures(lambda k: c.to_bytes(8, "big"),
+                                                        [(O.deserialize_g2(sig[bad].tobytes()), O.sk_to_pk(sks[bad]), tampered[bad])],
+                                                        want_gt=True)
+    assert not ok_o and gt == O.f12_to_bytes(gt_o)
+
+
 def test_verify_multiple_sharded_host_partials(eng):
     """The sharded form on one GPU: two shards through b3_verify_multiple_partial (host pointers) and
     b3_verify_multiple_partial_dev, combined by b3_combine_partials_dev, give the GT bytes / accept / global first_bad of
@@ -591,12 +617,13 @@ def test_verify_batch_single_key_modes(eng, item_kernel):
     assert len(a0) == 0 and len(s0) == 0
 
 
-def test_verify_batch_locates_bad_set_after_batch_reject(eng):
-    """The use the reference's callers make of per-item bits: verify_multiple rejects, the batch call names the culprit."""
+@pytest.mark.parametrize("n,bad", [(700, 123), (4200, 4100)], ids=["cta_per_item", "thread_per_item"])
+def test_verify_batch_locates_bad_set_after_batch_reject(eng, n, bad):
+    """The use the reference's callers make of per-item bits: verify_multiple rejects, the batch call names the culprit.
+    700 items take the CTA-per-item finishing kernel, 4200 the thread-per-item one (chosen by batch size)."""
     from milagro_bls_b200 import _lib
     import milagro_bls_b200 as mb
     rnd = random.Random(21)
-    n, bad = 700, 123
     sks = [rnd.randrange(1, O.r) for _ in range(n)]
     pk = eng.g1_mul_gen(sks)
     msgs = [bytes(rnd.getrandbits(8) for _ in range(32)) for _ in range(n)]
