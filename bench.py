@@ -47,8 +47,8 @@ FP_MULS = {"g1_aggregate": 1400, "g2_parse_subgroup_check": 1170, "hash_to_g2_af
 FP_MULS_PER_SET = 16400
 # what this implementation actually executes per set (inversion-free maps, bucket-method sum, split
 # Miller loop), in the same unit -- reported beside the SURVEY figure so the fraction cannot flatter the kernels
-EXEC_FP_MULS_PER_SET = 13400
-# DRAM bytes (read + write) per launch at the C4 shape from the committed `ncu --set full` captures (profiles/r1q_*_full.txt)
+EXEC_FP_MULS_PER_SET = 13200
+# DRAM bytes (read + write) per launch at the C4 shape from the committed `ncu --set full` captures (profiles/r1q_*_full.txt; unchanged kernels in r1r)
 NCU_TRAFFIC_BYTES = {"hash_to_g2_affine": 550400 + 6861312, "miller_accumulate": 162113792 + 4973056}
 CPU_PASSES = 4                # timed passes of the CPU baseline over its 2048-set sample (~10 s of CPU work per 4 cores)
 B3_EXTRA_PAIRS = 8            # window sums of the bucket-method signature sum, each its own pair
