@@ -58,7 +58,8 @@ const char* b3_stage_name(int stage);
 /* serial != 0: run the independent stages of a verification call one after another on the context's stream (for
  * per-stage timing); default 0: they overlap on internal streams, joined before the Miller loop */
 void b3_ctx_set_serial(b3_ctx* ctx, int serial);
-/* finishing kernel of b3_verify_batch: 0 = chosen by batch size (default), 1 = one CTA per item, 2 = one thread per item */
+/* finishing kernel of b3_verify_batch: 0 = chosen by batch size (default), 1 = one CTA per item, 2 = one thread per item,
+ * 3 = one lane pair per item */
 void b3_ctx_set_item_kernel(b3_ctx* ctx, int which);
 int b3_stage_count(void);
 
@@ -120,7 +121,7 @@ int b3_verify_multiple(b3_ctx*, const uint8_t* sigs192, const uint8_t* pks96, co
  *      accept[i] = the reference's bool; status[i] = B3_OK or the AmclError code of a malformed input of item i
  *      (B3_ERR_AGGREGATE_EMPTY_POINTS for an empty key list; accept[i] = 0 in every such case);
  *      gt576 (nullable, n x 576 B) = each item's FP12 after fexp, all-zero for items rejected before the pairing.
- *      One final exponentiation PER ITEM: one CTA per item for small batches, one thread per item from 4096 items. ---- */
+ *      One final exponentiation PER ITEM: one CTA per item below 2048 items, one lane pair per item above. ---- */
 #define B3_ITEM_VERIFY 0
 #define B3_ITEM_FAST_AGGREGATE 1
 #define B3_ITEM_PRE_AGGREGATED 2

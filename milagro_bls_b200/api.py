@@ -97,7 +97,7 @@ class Engine:
         self.L.b3_ctx_set_serial(self.handle, 1 if serial else 0)
 
     def set_item_kernel(self, which=0):
-        """Finishing kernel of verify_batch: 0 = by batch size, 1 = one CTA per item, 2 = one thread per item."""
+        """Finishing kernel of verify_batch: 0 = by batch size, 1 = CTA per item, 2 = thread per item, 3 = lane pair per item."""
         self.L.b3_ctx_set_item_kernel(self.handle, int(which))
 
     def stage_ms(self):

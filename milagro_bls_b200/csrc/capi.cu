@@ -48,7 +48,7 @@ struct b3_ctx {
     cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_fork2 = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
     int serial = 0;
-    int item_kernel = 0;            // b3_verify_batch finishing kernel: 0 = by batch size, 1 = CTA per item, 2 = thread per item
+    int item_kernel = 0;            // b3_verify_batch finishing kernel: 0 = by batch size, 1 = CTA per item, 2 = thread per item, 3 = lane pair per item
     // scratch (grown on demand, reused across calls)
     dev_buf in_a, in_b, in_c, in_d, in_e, in_f;      // staged host inputs
     dev_buf g1j, g1j2, g1a, g2a_sig, g2j, g2j2, g2j_h, g2a, g2q, g1pp, qinf, f12a, f12b, lines, status, ok, misc, outb;
@@ -618,7 +618,7 @@ extern "C" int b3_aggregate_verify(b3_ctx* ctx, const uint8_t sig192[192], const
 }
 
 // ---- batched per-item verification: n independent items, one accept bit each ------------------------
-#define B3_ITEMS_THREAD_MIN 4096
+#define B3_ITEMS_PAIR_MIN 2048
 static int verify_batch_core(b3_ctx* ctx, int mode, const uint8_t* d_sigs, const uint8_t* d_pks, const uint32_t* d_pk_off, size_t total_keys,
                              const uint8_t* d_msgs, const uint32_t* d_msg_off, size_t n, int32_t* d_accept, int32_t* d_status, uint8_t* d_gt) {
     CKR(ensure(ctx, ctx->g2a_sig, sizeof(g2_aff) * n));
@@ -679,10 +679,15 @@ static int verify_batch_core(b3_ctx* ctx, int mode, const uint8_t* d_sigs, const
     }
     CK(cudaEventRecord(ctx->ev[2], sm));
     sp = span_begin(ctx, ST_FINAL_EXP, sm);
-    // CTA per item: ~1.5 ms per wave of 2 x 148 items; thread per item: one item's latency (~20 ms) for any batch that fits the
-    // machine -- the crossover is near 4 k items
-    const bool per_thread = ctx->item_kernel == 2 || (ctx->item_kernel == 0 && n >= B3_ITEMS_THREAD_MIN);
-    if (per_thread)
+    // CTA per item: ~1.5 ms per wave of 2 x 148 items; lane pair per item: one item's latency (~12 ms) for any batch that fits
+    // the machine (17 ms at 16384 items, 33 ms at 32768) -- the crossover is near 2.3 k items
+    const bool per_thread = ctx->item_kernel == 2;          // measured slower than the lane-pair kernel at every batch size; kept selectable
+    const bool per_pair = ctx->item_kernel == 3 || (ctx->item_kernel == 0 && n >= B3_ITEMS_PAIR_MIN);
+    if (per_pair)
+        LAUNCH_ON(sm, k_items_finish_p, (unsigned)((2 * n + B3_ITEMS_PAIR_TPB - 1) / B3_ITEMS_PAIR_TPB), B3_ITEMS_PAIR_TPB, (const fp2*)ctx->lines.p,
+                  (const uint32_t*)ctx->qinf.p, (const g1_pp*)keys, n, (const int32_t*)d_st_sig, (const int32_t*)d_st_key,
+                  (const int32_t*)ctx->ok.p, mode == B3_ITEM_VERIFY ? 0 : 1, d_accept, d_status, d_gt);
+    else if (per_thread)
         LAUNCH_ON(sm, k_items_finish_t, (unsigned)((n + B3_ITEMS_TPB - 1) / B3_ITEMS_TPB), B3_ITEMS_TPB, (const fp2*)ctx->lines.p,
                   (const uint32_t*)ctx->qinf.p, (const g1_pp*)keys, n, (const int32_t*)d_st_sig, (const int32_t*)d_st_key,
                   (const int32_t*)ctx->ok.p, mode == B3_ITEM_VERIFY ? 0 : 1, d_accept, d_status, d_gt);

@@ -299,7 +299,6 @@ B3_FN_NOINLINE void pt_mul_u256_aff(jac<F>& r, const aff<F>& p, const uint32_t* 
 
 // ---- endomorphisms ------------------------------------------------------------------------------
 // (templates over the Fp2 representation F2: fp2 = one thread per value, fp2h = lane pairs, see fp2h.cuh)
-B3_FN void f2_const(fp2& r, const fp2& c) { r = c; }
 // psi on G2 (untwist-Frobenius-twist), Jacobian: (conj X * cx, conj Y * cy, conj Z)
 //   reference: A/ecp2.rs:538-548 with X = 1/FROB (A/ecp2.rs:785-789)
 template <class F2>

@@ -868,6 +868,68 @@ __global__ void __launch_bounds__(B3_ITEMS_TPB) k_items_finish_t(const fp2* __re
     status[i] = 0;
 }
 
+// ... and with a LANE PAIR per item (medium batches): the Fp6 / Fp12 tower and the final exponentiation are templates over the
+// Fp2 representation (tower.cuh, pairing.cuh), so the same chain runs with every Fp2 value split over two lanes (fp2h.cuh):
+// half the latency of the thread-per-item kernel and twice the threads.  Sparse products use the Karatsuba form
+// (fp12_mul_by_line: 14 Fp2 products, each 444 multiply-accumulates per lane).
+#define B3_ITEMS_PAIR_TPB 64
+__device__ __noinline__ void item_fold_line_p(fp12_t<fp2h>& f, bool& have, const fp2* __restrict__ src, const fp& ny, const fp& z3, const fp& xz) {
+    fp2h l0, l3, l5;
+    fp2h_load(l0, src[0]); fp2h_load(l3, src[1]); fp2h_load(l5, src[2]);
+    fp2_mul_fp(l0, l0, ny);
+    fp2_mul_fp(l3, l3, z3);
+    fp2_mul_fp(l5, l5, xz);
+    if (have) fp12_mul_by_line(f, l0, l3, l5);
+    else { fp12_from_line(f, l0, l3, l5); have = true; }
+}
+__global__ void __launch_bounds__(B3_ITEMS_PAIR_TPB) k_items_finish_p(const fp2* __restrict__ lines, const uint32_t* __restrict__ qinf,
+                                                                       const g1_pp* __restrict__ keys, size_t n, const int32_t* st_sig,
+                                                                       const int32_t* st_key, const int32_t* sig_ok, int reject_inf_key,
+                                                                       int32_t* accept, int32_t* status, uint8_t* gt_wire) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    if (i >= n) return;                                // both lanes of a pair leave together
+    const bool odd = pair_odd();
+    const int code = st_sig[i] ? st_sig[i] : st_key[i];
+    const g1_pp key = keys[i];
+    if (code != 0 || !sig_ok[i] || (reject_inf_key && key.inf)) {
+        if (!odd) { accept[i] = 0; status[i] = code; }
+        if (gt_wire) for (int b = odd ? 288 : 0; b < (odd ? 576 : 288); b++) gt_wire[576 * i + b] = 0;
+        return;
+    }
+    const bool valid0 = !qinf[i], valid1 = !(qinf[n + i] || key.inf);
+    const fp gy = G1_GEN_Y, one = FP_ONE, gx = G1_GEN_X;           // pair 0 = (sig_i, -G1): -(-y) = y
+    fp12_t<fp2h> f, g;
+    bool have = false;
+    const uint64_t x = B3_X_ABS;
+    const size_t np = 2 * n;
+    int a = B3_MILLER_DBL_SLOTS;
+#pragma unroll 1
+    for (int it = 0; it < B3_MILLER_DBL_SLOTS; it++) {
+        if (have) fp12_sqr(f, f);
+        const bool add = (x >> (62 - it)) & 1;
+#pragma unroll 1
+        for (int s = 0; s < (add ? 2 : 1); s++) {
+            const size_t slot = s == 0 ? (size_t)it : (size_t)a;
+            if (valid0) item_fold_line_p(f, have, lines + (slot * np + i) * 3, gy, one, gx);
+            if (valid1) item_fold_line_p(f, have, lines + (slot * np + n + i) * 3, key.ny, key.z3, key.xz);
+        }
+        if (add) a++;
+    }
+    if (!have) fp12_one(f);
+    fp12_conj(f, f);
+    final_exp(g, f);
+    const bool is_one = fp12_is_one(g);
+    if (gt_wire) {                                     // wire order w^0, w^3, w^1, w^4, w^2, w^5, each (re, im): this lane writes its half
+        const int order[6] = {0, 3, 1, 4, 2, 5};
+        for (int k = 0; k < 6; k++) {
+            fp t;
+            fp_from_mont(t, fp12_coef(g, order[k]).v);
+            fp_raw_to_be(gt_wire + 576 * i + 96 * k + (odd ? 48 : 0), t);
+        }
+    }
+    if (!odd) { accept[i] = is_one ? 1 : 0; status[i] = 0; }
+}
+
 // ------------------------------------------------------------------------------------------------ roofline microbenchmarks
 // Pure integer-multiply issue-rate probes: `iters` rounds of 8 independent chains per thread.
 __global__ void __launch_bounds__(256) k_imad_peak(uint32_t* out, int iters, uint32_t seed) {

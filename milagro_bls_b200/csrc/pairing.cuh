@@ -191,7 +191,8 @@ B3_FN void g1_pp_from_jac(g1_pp& r, const g1_jac& p) {
 }
 
 // dense Fp12 value of a line  l0 + l3 w^3 + l5 w^5
-B3_FN void fp12_from_line(fp12& f, const fp2& l0, const fp2& l3, const fp2& l5) {
+template <class F2>
+B3_FN void fp12_from_line(fp12_t<F2>& f, const F2& l0, const F2& l3, const F2& l5) {
     f.c0.c0 = l0; fp2_zero(f.c0.c1); fp2_zero(f.c0.c2);
     fp2_zero(f.c1.c0); f.c1.c1 = l3; f.c1.c2 = l5;
 }
@@ -222,9 +223,10 @@ B3_FN_NOINLINE void miller_loop_pair(fp12& f, const g2_aff& q, const g1_aff& p) 
 }
 
 // f^|x| for f in the cyclotomic subgroup (63 cyclotomic squarings + 5 multiplications)
-B3_FN_NOINLINE void fp12_pow_x_abs(fp12& r, const fp12& a, int shift) {
+template <class F2>
+B3_FN_NOINLINE void fp12_pow_x_abs(fp12_t<F2>& r, const fp12_t<F2>& a, int shift) {
     const uint64_t x = B3_X_ABS >> shift;
-    fp12 acc = a;
+    fp12_t<F2> acc = a;
     int top = 63 - shift;
     for (int i = top - 1; i >= 0; i--) {
         fp12_cyclo_sqr(acc, acc);
@@ -233,13 +235,16 @@ B3_FN_NOINLINE void fp12_pow_x_abs(fp12& r, const fp12& a, int shift) {
     r = acc;
 }
 // f^x (x negative): pow(|x|) then conjugate, as the reference does after every pow (A/pair.rs:490-529)
-B3_FN void fp12_pow_x(fp12& r, const fp12& a) { fp12_pow_x_abs(r, a, 0); fp12_conj(r, r); }
-B3_FN void fp12_pow_x_half(fp12& r, const fp12& a) { fp12_pow_x_abs(r, a, 1); fp12_conj(r, r); }
+template <class F2>
+B3_FN void fp12_pow_x(fp12_t<F2>& r, const fp12_t<F2>& a) { fp12_pow_x_abs(r, a, 0); fp12_conj(r, r); }
+template <class F2>
+B3_FN void fp12_pow_x_half(fp12_t<F2>& r, const fp12_t<F2>& a) { fp12_pow_x_abs(r, a, 1); fp12_conj(r, r); }
 
 // Final exponentiation: exactly the exponent 3 (p^12 - 1) / r the reference computes
 // (easy part (p^6 - 1)(p^2 + 1), hard part = Ghammam-Fouotsa chain of A/pair.rs:485-539).
-B3_FN_NOINLINE void final_exp(fp12& r, const fp12& m) {
-    fp12 t, y0, y1, y2, y3, rr;
+template <class F2>
+B3_FN_NOINLINE void final_exp(fp12_t<F2>& r, const fp12_t<F2>& m) {
+    fp12_t<F2> t, y0, y1, y2, y3, rr;
     fp12_inv(t, m);
     fp12_conj(rr, m);
     fp12_mul(rr, rr, t);                // m^(p^6 - 1)

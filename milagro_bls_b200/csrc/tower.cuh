@@ -10,12 +10,18 @@
 #pragma once
 #include "fp.cuh"
 
-struct fp6 {
-    fp2 c0, c1, c2;
+// The Fp6 / Fp12 layers are templates over the Fp2 representation F2: fp2 (one thread per value; fp6 / fp12 below) or
+// fp2h (lane pairs, fp2h.cuh) -- the same way the point formulas of curve.cuh / pairing.cuh are.
+template <class F2>
+struct fp6_t {
+    F2 c0, c1, c2;
 };
-struct fp12 {
-    fp6 c0, c1;
+template <class F2>
+struct fp12_t {
+    fp6_t<F2> c0, c1;
 };
+typedef fp6_t<fp2> fp6;
+typedef fp12_t<fp2> fp12;
 
 // ---------------------------------------------------------------- Fp2
 B3_FN void fp2_add(fp2& r, const fp2& a, const fp2& b) { fp_add(r.c0, a.c0, b.c0); fp_add(r.c1, a.c1, b.c1); }
@@ -178,20 +184,28 @@ B3_FN_NOINLINE bool fp2_sqrt_ratio_or_z(fp2& r, const fp2& u, const fp2& v) {
     return sq;
 }
 
+// a constant of Fp2 in the representation F2 (the lane-pair overload picks this lane's half, fp2h.cuh)
+B3_FN void f2_const(fp2& r, const fp2& c) { r = c; }
+
 // ---------------------------------------------------------------- Fp6
-B3_FN void fp6_add(fp6& r, const fp6& a, const fp6& b) { fp2_add(r.c0, a.c0, b.c0); fp2_add(r.c1, a.c1, b.c1); fp2_add(r.c2, a.c2, b.c2); }
-B3_FN void fp6_sub(fp6& r, const fp6& a, const fp6& b) { fp2_sub(r.c0, a.c0, b.c0); fp2_sub(r.c1, a.c1, b.c1); fp2_sub(r.c2, a.c2, b.c2); }
-B3_FN void fp6_neg(fp6& r, const fp6& a) { fp2_neg(r.c0, a.c0); fp2_neg(r.c1, a.c1); fp2_neg(r.c2, a.c2); }
+template <class F2>
+B3_FN void fp6_add(fp6_t<F2>& r, const fp6_t<F2>& a, const fp6_t<F2>& b) { fp2_add(r.c0, a.c0, b.c0); fp2_add(r.c1, a.c1, b.c1); fp2_add(r.c2, a.c2, b.c2); }
+template <class F2>
+B3_FN void fp6_sub(fp6_t<F2>& r, const fp6_t<F2>& a, const fp6_t<F2>& b) { fp2_sub(r.c0, a.c0, b.c0); fp2_sub(r.c1, a.c1, b.c1); fp2_sub(r.c2, a.c2, b.c2); }
+template <class F2>
+B3_FN void fp6_neg(fp6_t<F2>& r, const fp6_t<F2>& a) { fp2_neg(r.c0, a.c0); fp2_neg(r.c1, a.c1); fp2_neg(r.c2, a.c2); }
 // * v : (c0, c1, c2) -> (xi c2, c0, c1)
-B3_FN void fp6_mul_v(fp6& r, const fp6& a) {
-    fp2 t;
+template <class F2>
+B3_FN void fp6_mul_v(fp6_t<F2>& r, const fp6_t<F2>& a) {
+    F2 t;
     fp2_mul_xi(t, a.c2);
     r.c2 = a.c1;
     r.c1 = a.c0;
     r.c0 = t;
 }
-B3_FN_NOINLINE void fp6_mul(fp6& r, const fp6& a, const fp6& b) {
-    fp2 v0, v1, v2, t0, t1, t2;
+template <class F2>
+B3_FN_NOINLINE void fp6_mul(fp6_t<F2>& r, const fp6_t<F2>& a, const fp6_t<F2>& b) {
+    F2 v0, v1, v2, t0, t1, t2;
     fp2_mul(v0, a.c0, b.c0);
     fp2_mul(v1, a.c1, b.c1);
     fp2_mul(v2, a.c2, b.c2);
@@ -212,7 +226,7 @@ B3_FN_NOINLINE void fp6_mul(fp6& r, const fp6& a, const fp6& b) {
     fp2_mul_xi(t2, v2);
     fp2_add(t1, t1, t2);
     // c2 = (a0+a2)(b0+b2) - v0 - v2 + v1
-    fp2 u0, u1;
+    F2 u0, u1;
     fp2_add(u0, a.c0, a.c2);
     fp2_add(u1, b.c0, b.c2);
     fp2_mul(u0, u0, u1);
@@ -222,14 +236,17 @@ B3_FN_NOINLINE void fp6_mul(fp6& r, const fp6& a, const fp6& b) {
     r.c0 = t0;
     r.c1 = t1;
 }
-B3_FN void fp6_sqr(fp6& r, const fp6& a) { fp6_mul(r, a, a); }
+template <class F2>
+B3_FN void fp6_sqr(fp6_t<F2>& r, const fp6_t<F2>& a) { fp6_mul(r, a, a); }
 // a * (b0, 0, 0)
-B3_FN void fp6_mul_fp2(fp6& r, const fp6& a, const fp2& b0) {
+template <class F2>
+B3_FN void fp6_mul_fp2(fp6_t<F2>& r, const fp6_t<F2>& a, const F2& b0) {
     fp2_mul(r.c0, a.c0, b0); fp2_mul(r.c1, a.c1, b0); fp2_mul(r.c2, a.c2, b0);
 }
 // a * (0, b1, b2)
-B3_FN_NOINLINE void fp6_mul_by_12(fp6& r, const fp6& a, const fp2& b1, const fp2& b2) {
-    fp2 v1, v2, t0, t1, t2;
+template <class F2>
+B3_FN_NOINLINE void fp6_mul_by_12(fp6_t<F2>& r, const fp6_t<F2>& a, const F2& b1, const F2& b2) {
+    F2 v1, v2, t0, t1, t2;
     fp2_mul(v1, a.c1, b1);
     fp2_mul(v2, a.c2, b2);
     // c0 = xi (a1 b2 + a2 b1) = xi((a1+a2)(b1+b2) - v1 - v2)
@@ -248,8 +265,9 @@ B3_FN_NOINLINE void fp6_mul_by_12(fp6& r, const fp6& a, const fp2& b1, const fp2
     r.c0 = t0;
     r.c1 = t1;
 }
-B3_FN_NOINLINE void fp6_inv(fp6& r, const fp6& a) {
-    fp2 A, B, C, t, F;
+template <class F2>
+B3_FN_NOINLINE void fp6_inv(fp6_t<F2>& r, const fp6_t<F2>& a) {
+    F2 A, B, C, t, F;
     fp2_sqr(A, a.c0); fp2_mul(t, a.c1, a.c2); fp2_mul_xi(t, t); fp2_sub(A, A, t);      // a0^2 - xi a1 a2
     fp2_sqr(B, a.c2); fp2_mul_xi(B, B); fp2_mul(t, a.c0, a.c1); fp2_sub(B, B, t);      // xi a2^2 - a0 a1
     fp2_sqr(C, a.c1); fp2_mul(t, a.c0, a.c2); fp2_sub(C, C, t);                        // a1^2 - a0 a2
@@ -261,20 +279,27 @@ B3_FN_NOINLINE void fp6_inv(fp6& r, const fp6& a) {
 }
 
 // ---------------------------------------------------------------- Fp12
-B3_FN void fp12_one(fp12& r) {
+template <class F2>
+B3_FN void fp12_one(fp12_t<F2>& r) {
     fp2_one(r.c0.c0); fp2_zero(r.c0.c1); fp2_zero(r.c0.c2);
     fp2_zero(r.c1.c0); fp2_zero(r.c1.c1); fp2_zero(r.c1.c2);
 }
-B3_FN bool fp12_eq(const fp12& a, const fp12& b) {
+template <class F2>
+B3_FN bool fp12_eq(const fp12_t<F2>& a, const fp12_t<F2>& b) {
     return fp2_eq(a.c0.c0, b.c0.c0) && fp2_eq(a.c0.c1, b.c0.c1) && fp2_eq(a.c0.c2, b.c0.c2) &&
            fp2_eq(a.c1.c0, b.c1.c0) && fp2_eq(a.c1.c1, b.c1.c1) && fp2_eq(a.c1.c2, b.c1.c2);
 }
-B3_FN bool fp12_is_one(const fp12& a) {
-    return fp_eq(a.c0.c0.c0, FP_ONE) && fp_is_zero(a.c0.c0.c1) && fp2_is_zero(a.c0.c1) && fp2_is_zero(a.c0.c2) &&
-           fp2_is_zero(a.c1.c0) && fp2_is_zero(a.c1.c1) && fp2_is_zero(a.c1.c2);
+template <class F2>
+B3_FN bool fp12_is_one(const fp12_t<F2>& a) {
+    F2 one;
+    fp2_one(one);
+    const bool e0 = fp2_eq(a.c0.c0, one), z1 = fp2_is_zero(a.c0.c1), z2 = fp2_is_zero(a.c0.c2);      // (lane pairs: every
+    const bool z3 = fp2_is_zero(a.c1.c0), z4 = fp2_is_zero(a.c1.c1), z5 = fp2_is_zero(a.c1.c2);      //  test runs on both lanes)
+    return e0 && z1 && z2 && z3 && z4 && z5;
 }
-B3_FN_NOINLINE void fp12_mul(fp12& r, const fp12& a, const fp12& b) {
-    fp6 t0, t1, s0, s1;
+template <class F2>
+B3_FN_NOINLINE void fp12_mul(fp12_t<F2>& r, const fp12_t<F2>& a, const fp12_t<F2>& b) {
+    fp6_t<F2> t0, t1, s0, s1;
     fp6_mul(t0, a.c0, b.c0);
     fp6_mul(t1, a.c1, b.c1);
     fp6_add(s0, a.c0, a.c1);
@@ -286,8 +311,9 @@ B3_FN_NOINLINE void fp12_mul(fp12& r, const fp12& a, const fp12& b) {
     fp6_add(r.c0, t0, t1);
 }
 // complex squaring: 2 Fp6 mults
-B3_FN_NOINLINE void fp12_sqr(fp12& r, const fp12& a) {
-    fp6 ab, s, t;
+template <class F2>
+B3_FN_NOINLINE void fp12_sqr(fp12_t<F2>& r, const fp12_t<F2>& a) {
+    fp6_t<F2> ab, s, t;
     fp6_mul(ab, a.c0, a.c1);
     fp6_add(s, a.c0, a.c1);
     fp6_mul_v(t, a.c1);
@@ -299,9 +325,11 @@ B3_FN_NOINLINE void fp12_sqr(fp12& r, const fp12& a) {
     fp6_add(r.c1, ab, ab);
 }
 // conj = p^6 Frobenius: w -> -w
-B3_FN void fp12_conj(fp12& r, const fp12& a) { r.c0 = a.c0; fp6_neg(r.c1, a.c1); }
-B3_FN_NOINLINE void fp12_inv(fp12& r, const fp12& a) {
-    fp6 t0, t1;
+template <class F2>
+B3_FN void fp12_conj(fp12_t<F2>& r, const fp12_t<F2>& a) { r.c0 = a.c0; fp6_neg(r.c1, a.c1); }
+template <class F2>
+B3_FN_NOINLINE void fp12_inv(fp12_t<F2>& r, const fp12_t<F2>& a) {
+    fp6_t<F2> t0, t1;
     fp6_sqr(t0, a.c0);
     fp6_sqr(t1, a.c1);
     fp6_mul_v(t1, t1);
@@ -312,12 +340,13 @@ B3_FN_NOINLINE void fp12_inv(fp12& r, const fp12& a) {
     fp6_neg(r.c1, t1);
 }
 // multiply by a sparse line  l0 + l3 w^3 + l5 w^5  =  (l0,0,0) + (0,l3,l5) w
-B3_FN_NOINLINE void fp12_mul_by_line(fp12& f, const fp2& l0, const fp2& l3, const fp2& l5) {
-    fp6 t0, t1, s;
+template <class F2>
+B3_FN_NOINLINE void fp12_mul_by_line(fp12_t<F2>& f, const F2& l0, const F2& l3, const F2& l5) {
+    fp6_t<F2> t0, t1, s;
     fp6_mul_fp2(t0, f.c0, l0);                       // f0 * L0
     fp6_mul_by_12(t1, f.c1, l3, l5);                 // f1 * L1
     fp6_add(s, f.c0, f.c1);
-    fp6 L;
+    fp6_t<F2> L;
     L.c0 = l0; L.c1 = l3; L.c2 = l5;
     fp6_mul(s, s, L);                                // (f0+f1)(L0+L1)
     fp6_sub(s, s, t0);
@@ -372,40 +401,46 @@ B3_FN_NOINLINE void fp12_mul_by_line_dot(fp12& r, const fp12& f, const line_ops&
 }
 
 // p-power Frobenius: f_k -> conj(f_k) * GAMMA1[k]
-B3_FN fp2& fp12_coef(fp12& a, int k) {
+template <class F2>
+B3_FN F2& fp12_coef(fp12_t<F2>& a, int k) {
     return (k & 1) ? ((k == 1) ? a.c1.c0 : (k == 3) ? a.c1.c1 : a.c1.c2)
                    : ((k == 0) ? a.c0.c0 : (k == 2) ? a.c0.c1 : a.c0.c2);
 }
-B3_FN const fp2& fp12_coef(const fp12& a, int k) {
+template <class F2>
+B3_FN const F2& fp12_coef(const fp12_t<F2>& a, int k) {
     return (k & 1) ? ((k == 1) ? a.c1.c0 : (k == 3) ? a.c1.c1 : a.c1.c2)
                    : ((k == 0) ? a.c0.c0 : (k == 2) ? a.c0.c1 : a.c0.c2);
 }
-B3_FN_NOINLINE void fp12_frob(fp12& r, const fp12& a) {
+template <class F2>
+B3_FN_NOINLINE void fp12_frob(fp12_t<F2>& r, const fp12_t<F2>& a) {
     for (int k = 0; k < 6; k++) {
-        fp2 t;
+        F2 t;
         fp2_conj(t, fp12_coef(a, k));
         if (k == 0) fp12_coef(r, 0) = t;
-        else fp2_mul(fp12_coef(r, k), t, FROB_GAMMA1[k]);
+        else { F2 g; f2_const(g, FROB_GAMMA1[k]); fp2_mul(fp12_coef(r, k), t, g); }
     }
 }
-B3_FN_NOINLINE void fp12_frob2(fp12& r, const fp12& a) {
+template <class F2>
+B3_FN_NOINLINE void fp12_frob2(fp12_t<F2>& r, const fp12_t<F2>& a) {
     fp12_coef(r, 0) = fp12_coef(a, 0);
     for (int k = 1; k < 6; k++) fp2_mul_fp(fp12_coef(r, k), fp12_coef(a, k), FROB_GAMMA2[k]);
 }
-B3_FN_NOINLINE void fp12_frob3(fp12& r, const fp12& a) {
+template <class F2>
+B3_FN_NOINLINE void fp12_frob3(fp12_t<F2>& r, const fp12_t<F2>& a) {
     for (int k = 0; k < 6; k++) {
-        fp2 t;
+        F2 t;
         fp2_conj(t, fp12_coef(a, k));
         if (k == 0) fp12_coef(r, 0) = t;
-        else fp2_mul(fp12_coef(r, k), t, FROB_GAMMA3[k]);
+        else { F2 g; f2_const(g, FROB_GAMMA3[k]); fp2_mul(fp12_coef(r, k), t, g); }
     }
 }
 
 // Granger-Scott squaring for elements of the cyclotomic subgroup (after the easy part of fexp).
 // Uses the Fp4 = Fp2[s]/(s^2 - xi) sub-structure with s = w^3: pairs (f0,f3), (f1,f4), (f2,f5).
-B3_FN_NOINLINE void fp4_sqr_parts(fp2& r0, fp2& r1, const fp2& a, const fp2& b) {
+template <class F2>
+B3_FN_NOINLINE void fp4_sqr_parts(F2& r0, F2& r1, const F2& a, const F2& b) {
     // (a + b s)^2 = (a^2 + xi b^2) + (2ab) s
-    fp2 t0, t1, t2;
+    F2 t0, t1, t2;
     fp2_sqr(t0, a);
     fp2_sqr(t1, b);
     fp2_add(t2, a, b);
@@ -415,12 +450,13 @@ B3_FN_NOINLINE void fp4_sqr_parts(fp2& r0, fp2& r1, const fp2& a, const fp2& b) 
     fp2_mul_xi(t1, t1);
     fp2_add(r0, t0, t1);
 }
-B3_FN_NOINLINE void fp12_cyclo_sqr(fp12& r, const fp12& a) {
+template <class F2>
+B3_FN_NOINLINE void fp12_cyclo_sqr(fp12_t<F2>& r, const fp12_t<F2>& a) {
     // basis: a = g0 + g1 y + g2 y^2 with y = w (y^3 = s = w^3), g0 = (f0, f3), g1 = (f1, f4), g2 = (f2, f5) in Fp4.
     // Granger-Scott: with A = g0^2, B = g2^2 * s, C = g1^2 :
     //   r.g0 = 3A - 2 conj(g0);  r.g1 = 3B + 2 conj(g1);  r.g2 = 3C - 2 conj(g2)     (conj: s -> -s)
-    fp2 A0, A1, B0, B1, C0, C1, t;
-    const fp2 &f0 = fp12_coef(a, 0), &f1 = fp12_coef(a, 1), &f2 = fp12_coef(a, 2),
+    F2 A0, A1, B0, B1, C0, C1, t;
+    const F2 &f0 = fp12_coef(a, 0), &f1 = fp12_coef(a, 1), &f2 = fp12_coef(a, 2),
               &f3 = fp12_coef(a, 3), &f4 = fp12_coef(a, 4), &f5 = fp12_coef(a, 5);
     fp4_sqr_parts(A0, A1, f0, f3);
     fp4_sqr_parts(C0, C1, f1, f4);
@@ -429,7 +465,7 @@ B3_FN_NOINLINE void fp12_cyclo_sqr(fp12& r, const fp12& a) {
     fp2_mul_xi(t, B1);
     B1 = B0;
     B0 = t;
-    fp2 o0, o1, o2, o3, o4, o5;
+    F2 o0, o1, o2, o3, o4, o5;
     // g0' = 3A - 2 conj(g0) = (3A0 - 2 f0) + (3A1 + 2 f3) s
     fp2_sub(t, A0, f0); fp2_dbl(t, t); fp2_add(o0, t, A0);
     fp2_add(t, A1, f3); fp2_dbl(t, t); fp2_add(o3, t, A1);

@@ -1,5 +1,5 @@
 """Timing helper for b3_verify_batch (per-item accept bits): n items, device-resident inputs, CUDA-event time of the call.
-usage: python profiles/run_batch.py [n_items] [keys_per_item] [reps] [item_kernel: 0 auto, 1 CTA per item, 2 thread per item]"""
+usage: python profiles/run_batch.py [n_items] [keys_per_item] [reps] [item_kernel: 0 auto, 1 CTA per item, 2 thread per item, 3 lane pair per item]"""
 import os
 import sys
 import random

@@ -555,9 +555,9 @@ def test_verify_multiple_sharded_host_partials(eng):
             assert not ok and fb == 3                                   # global index of the non-subgroup signature
 
 
-@pytest.fixture(params=[1, 2], ids=["cta_per_item", "thread_per_item"])
+@pytest.fixture(params=[1, 2, 3], ids=["cta_per_item", "thread_per_item", "lane_pair_per_item"])
 def item_kernel(eng, request):
-    """Both finishing kernels of b3_verify_batch on the same small batches (the default picks by batch size)."""
+    """All three finishing kernels of b3_verify_batch on the same small batches (the default picks by batch size)."""
     eng.set_item_kernel(request.param)
     yield request.param
     eng.set_item_kernel(0)
@@ -617,10 +617,10 @@ def test_verify_batch_single_key_modes(eng, item_kernel):
     assert len(a0) == 0 and len(s0) == 0
 
 
-@pytest.mark.parametrize("n,bad", [(700, 123), (4200, 4100)], ids=["cta_per_item", "thread_per_item"])
+@pytest.mark.parametrize("n,bad", [(700, 123), (4200, 4100)], ids=["cta_per_item", "lane_pair_per_item"])
 def test_verify_batch_locates_bad_set_after_batch_reject(eng, n, bad):
     """The use the reference's callers make of per-item bits: verify_multiple rejects, the batch call names the culprit.
-    700 items take the CTA-per-item finishing kernel, 4200 the thread-per-item one (chosen by batch size)."""
+    700 items take the CTA-per-item finishing kernel, 4200 the lane-pair one (chosen by batch size)."""
     from milagro_bls_b200 import _lib
     import milagro_bls_b200 as mb
     rnd = random.Random(21)
