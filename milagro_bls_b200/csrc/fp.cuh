@@ -369,6 +369,67 @@ __device__ __forceinline__ void fp_dot6_rs(fp& r, const fp (&a)[6], const fp* b0
 }
 #endif
 
+// Montgomery SQUARING  r = a^2 / 2^384 mod p  (a < p), row-wise with the same interleaved reduction as fp_mul_inl, but using
+//   a^2 = sum_i a_i 2^(32 i) * ( a_i 2^(32 i) + 2 sum_{j>i} a_j 2^(32 j) ):
+// row i adds a_i times the limbs j >= i of that bracket only -- a_i itself at j = i, a_(i+1) << 1 at j = i + 1 and the limbs
+// d_j = (a_j << 1) | (a_(j-1) >> 31) of 2a above (2a < 2^382 has no 13th limb) -- i.e. 12 - i products instead of 12:
+// 78 + 144 + 12 = 234 multiply-accumulates instead of 300.  Every contribution to limb k (pairs i + j = k) is added in a
+// row min(i, j) <= k, before limb k is reduced, so the interleaved reduction stays valid.  Bounds: the running value
+// obeys W' < W / 2^32 + 2a + p, hence W < 3p (1 + 2^-32) < 2^383 as in fp_mul2_inl (same accumulator shapes, same dropped
+// carries), and the result (a^2 + m p) / 2^384 < 1.11 p needs the one final subtraction.
+template <int I>
+B3_FN void b3_sqr_row(uint32_t* E, uint32_t* O, const uint32_t* a, const uint32_t* d) {
+#define B3_SQW(j) ((j) == I ? a[(j)] : (j) == I + 1 ? (a[(j)] << 1) : d[(j)])
+    const uint32_t ai = a[I];
+    if (I == 0) {
+#pragma unroll
+        for (int j = 0; j < 12; j += 2) mul_wide(O[j], O[j + 1], B3_SQW(j + 1), ai);
+#pragma unroll
+        for (int j = 0; j < 12; j += 2) mul_wide(E[j], E[j + 1], B3_SQW(j), ai);
+    } else {
+        E[0] = add_cc(E[0], O[1]);
+        // O = (O >> 64) + products at the odd window positions >= I, carry in from the addition above
+#pragma unroll
+        for (int j = 0; j < 10; j += 2) {
+            if (j + 1 >= I) madc_wide_cc_in(O[j], O[j + 1], B3_SQW(j + 1), ai, O[j + 2], O[j + 3]);
+            else { O[j] = addc_cc(O[j + 2], 0); O[j + 1] = addc_cc(O[j + 3], 0); }
+        }
+        madc_wide_last(O[10], O[11], B3_SQW(11), ai);                  // position 11 >= I always
+        // E += products at the even window positions >= I
+        if (I <= 10) {
+            const int j0 = (I + 1) & ~1;
+            mad_wide_cc(E[j0], E[j0 + 1], B3_SQW(j0), ai);
+#pragma unroll
+            for (int j = j0 + 2; j < 12; j += 2) madc_wide_cc(E[j], E[j + 1], B3_SQW(j), ai);
+            O[11] = addc(O[11], 0);
+        }
+    }
+    uint32_t m = E[0] * FP_PINV32;
+    b3_mad_row(O, FP_P.l + 1, m);
+    b3_mad_row(E, FP_P.l, m);
+    O[11] = addc(O[11], 0);
+#undef B3_SQW
+}
+B3_FN void fp_sqr_inl(fp& r, const fp& a) {
+    uint32_t even[12], odd[12], av[12], d[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) av[i] = a.l[i];
+    d[0] = av[0] << 1;
+#pragma unroll
+    for (int i = 1; i < 12; i++) d[i] = (av[i] << 1) | (av[i - 1] >> 31);
+    b3_sqr_row<0>(even, odd, av, d);  b3_sqr_row<1>(odd, even, av, d);
+    b3_sqr_row<2>(even, odd, av, d);  b3_sqr_row<3>(odd, even, av, d);
+    b3_sqr_row<4>(even, odd, av, d);  b3_sqr_row<5>(odd, even, av, d);
+    b3_sqr_row<6>(even, odd, av, d);  b3_sqr_row<7>(odd, even, av, d);
+    b3_sqr_row<8>(even, odd, av, d);  b3_sqr_row<9>(odd, even, av, d);
+    b3_sqr_row<10>(even, odd, av, d); b3_sqr_row<11>(odd, even, av, d);
+    even[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+    for (int i = 1; i < 11; i++) even[i] = addc_cc(even[i], odd[i + 1]);
+    even[11] = addc(even[11], 0);
+    fp_final_sub(r, even);
+}
+
 // Out-of-line multipliers take and return their operands BY VALUE: ptxas then passes them in registers, and the
 // callers' field elements never have their address taken, so they stay in registers instead of the local-memory
 // stack (by-reference noinline calls put every operand through LDL/STL: 113 M local loads in the first Miller
@@ -377,7 +438,8 @@ B3_FN_NOINLINE fp fp_mul_v(fp a, fp b) { fp r; fp_mul_inl(r, a, b); return r; }
 B3_FN_NOINLINE fp fp_mul2_v(fp a1, fp b1, fp a2, fp b2) { fp r; fp_mul2_inl(r, a1, b1, a2, b2); return r; }
 B3_FN void fp_mul2(fp& r, const fp& a1, const fp& b1, const fp& a2, const fp& b2) { r = fp_mul2_v(a1, b1, a2, b2); }
 B3_FN void fp_mul(fp& r, const fp& a, const fp& b) { r = fp_mul_v(a, b); }
-B3_FN void fp_sqr(fp& r, const fp& a) { r = fp_mul_v(a, a); }
+B3_FN_NOINLINE fp fp_sqr_v(fp a) { fp r; fp_sqr_inl(r, a); return r; }
+B3_FN void fp_sqr(fp& r, const fp& a) { r = fp_sqr_v(a); }
 
 // Montgomery form <-> canonical
 B3_FN void fp_to_mont(fp& r, const fp& a) { fp_mul(r, FP_R2, a); }       // a any 384-bit value

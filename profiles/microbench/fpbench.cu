@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(128) k_bench(uint32_t* out, int iters, uint32_
         if (V == 9) { fp t; pair_xchg(t, x); fp_add(x, t, y); }
         if (V == 10) { fp2 a, b; a.c0 = x; a.c1 = z; b.c0 = y; b.c1 = w; a = fp2_mul_v(a, b); x = a.c0; z = a.c1; }
         if (V == 11) { fp2 a; a.c0 = x; a.c1 = z; a = fp2_sqr_v(a); x = a.c0; z = a.c1; }
+        if (V == 12) { x = fp_sqr_v(x); }
     }
     long long t1 = clock64();
     uint32_t r = 0;
@@ -80,5 +81,6 @@ int main() {
     run<9>("pair_xchg + fp_add", N, 0);
     run<10>("fp2_mul_v (1 thread)", N, 888);
     run<11>("fp2_sqr_v (1 thread)", N, 600);
+    run<12>("fp_sqr_v (dedicated, 234 MACs)", N, 234);
     return 0;
 }

@@ -36,6 +36,10 @@ void hs_fp_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
 void hs_fp_mont_mul_raw(const uint8_t* a, const uint8_t* b, uint8_t* out) {
     fp x, y, r; fp_raw_from_be(x, a); fp_raw_from_be(y, b); fp_mul(r, x, y); fp_raw_to_be(out, r);
 }
+// raw Montgomery square a^2 / 2^384 mod p of a plain integer a < p (limb patterns chosen by the test)
+void hs_fp_sqr_raw(const uint8_t* a, uint8_t* out) {
+    fp x, r; fp_raw_from_be(x, a); fp_sqr(r, x); fp_raw_to_be(out, r);
+}
 void hs_fp2_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     fp2 x, y, r;
     fp2_in(x, a); fp2_in(y, b);

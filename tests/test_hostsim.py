@@ -84,6 +84,24 @@ def test_fp_mont_mul_raw_edges(hs):
         assert int.from_bytes(out.raw, "big") == a * b * Rinv % p
 
 
+def test_fp_sqr_raw_limb_patterns(hs):
+    """Dedicated Montgomery squaring (fp_sqr_inl: symmetric rows over 2a): limb patterns that exercise the doubling carries
+    between limbs (top bits set), all-ones limbs, single limbs, and random values -- against a^2 / 2^384 mod p."""
+    Rinv = pow(1 << 384, -1, p)
+    pats = [0, 1, p - 1, p - 2, (1 << 380) - 1, (1 << 381) - 1 - ((1 << 381) - 1) // p * 0]
+    pats = [v for v in pats if v < p]
+    pats += [sum(0x80000000 << (32 * i) for i in range(11)), sum(0xffffffff << (32 * i) for i in range(11)) | (0x1a01 << 368) - 0,
+             sum(0x80000001 << (32 * i) for i in range(0, 11, 2)), sum(0xffffffff << (32 * i) for i in range(1, 11, 2))]
+    pats += [1 << (32 * i) for i in range(12) if (1 << (32 * i)) < p] + [(1 << (32 * i + 31)) for i in range(11)]
+    pats += [0xffffffff << (32 * i) for i in range(11)]
+    pats += [rnd.getrandbits(384) % p for _ in range(300)]
+    for a in pats:
+        a %= p
+        out = ctypes.create_string_buffer(48)
+        hs.hs_fp_sqr_raw(a.to_bytes(48, "big"), out)
+        assert int.from_bytes(out.raw, "big") == a * a * Rinv % p, hex(a)
+
+
 def test_fp2_ops(hs):
     for _ in range(50):
         a, b = rfp2(), rfp2()
