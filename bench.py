@@ -48,8 +48,8 @@ FP_MULS_PER_SET = 16400
 # what this implementation actually executes per set (inversion-free maps, bucket-method sum, split
 # Miller loop), in the same unit -- reported beside the SURVEY figure so the fraction cannot flatter the kernels
 EXEC_FP_MULS_PER_SET = 13200
-# DRAM bytes (read + write) per launch at the C4 shape from the committed `ncu --set full` captures (profiles/r1q_*_full.txt; unchanged kernels in r1r)
-NCU_TRAFFIC_BYTES = {"hash_to_g2_affine": 550400 + 6861312, "miller_accumulate": 162113792 + 4973056}
+# DRAM bytes (read + write) per launch at the C4 shape from the committed `ncu --set full` captures (profiles/r1s_h2c_full.txt, r1q_accum_full.txt)
+NCU_TRAFFIC_BYTES = {"hash_to_g2_affine": 534016 + 6311424, "miller_accumulate": 162113792 + 4973056}
 CPU_PASSES = 4                # timed passes of the CPU baseline over its 2048-set sample (~10 s of CPU work per 4 cores)
 B3_EXTRA_PAIRS = 8            # window sums of the bucket-method signature sum, each its own pair
 BYTES_PER_SET = KEYS_PER_SET * 96 + 192 + MSG_LEN + 8          # algorithmic HBM bytes read per set
@@ -569,7 +569,7 @@ def _bench_lanes(eng, lanes, args, world, rank, local_rank, dev):
         roofline = {"bound": "imad", "kernel": dom, "achieved": achieved / 1e9, "peak": peak_mac / 1e9, "unit": "GMAC/s (32x32->64 multiply-accumulate)",
                     "frac": achieved / peak_mac,
                     "traffic": NCU_TRAFFIC_BYTES.get(dom) if (n == SETS_PER_GPU and nk == KEYS_PER_SET) else None,
-                    "traffic_note": "DRAM bytes read + written per launch, ncu --set full capture (profiles/r1q_h2c_full.txt); the kernel is "
+                    "traffic_note": "DRAM bytes read + written per launch, ncu --set full capture (profiles/r1s_h2c_full.txt); the kernel is "
                                     "bound by the integer multiply pipe, not HBM",
                     "kernel_ms": dom_ms, "algorithmic_fp_muls_per_unit": FP_MULS[dom], "macs_per_fp_mul": MACS_PER_FP_MUL, "units_per_launch": units,
                     "peak_source": "live probe b3_imad_peak(wide=1): IMAD.WIDE carry chains, all SMs",
