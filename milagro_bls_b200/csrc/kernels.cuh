@@ -15,6 +15,9 @@
 #define B3_MIN_CTAS 2
 #endif
 #define B3_LBH __launch_bounds__(B3_TPB, B3_MIN_CTAS)
+#ifndef B3_H2C_CTAS
+#define B3_H2C_CTAS 2
+#endif
 
 // ------------------------------------------------------------------------------------------------ parsing
 // G1 uncompressed wire -> Jacobian (Z = 1, or infinity).  status: per-item AmclError code.
@@ -496,7 +499,7 @@ __global__ void __launch_bounds__(B3_TPB) k_g2_aff_to_wire(const g2_aff* in, siz
 // Two threads per message.  Phase 1: each lane maps ONE of the two field elements to the curve (SSWU + 3-isogeny,
 // single-thread Fp2 arithmetic: the square roots are chains of Fp operations).  Phase 2: the two points are
 // redistributed into lane-pair form and the pair adds them and clears the cofactor together.
-__global__ void B3_LBH k_hash_to_g2(const uint8_t* __restrict__ msgs, const uint32_t* __restrict__ off, size_t n,
+__global__ void __launch_bounds__(B3_TPB, B3_H2C_CTAS) k_hash_to_g2(const uint8_t* __restrict__ msgs, const uint32_t* __restrict__ off, size_t n,
                                                        const uint8_t* __restrict__ dst, uint32_t dst_len, g2_jac* out) {
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     if (i >= n) return;
