@@ -321,6 +321,50 @@ def test_aggregate_verify_cases(eng):
     assert mb.AggregateSignature(g2w(agg2)).aggregate_verify(msgs2, pks[:3])
 
 
+def test_baseline_config_shapes_c1_c2_c3(eng):
+    """BASELINE.json configs at their full sizes, accept bit AND GT bytes against the C oracle (itself pinned to the Python
+    oracle and the golden vectors, tests/test_oracle_c.py): C1 = one signature on b"cats"; C2 = fast_aggregate_verify of one
+    message under 512 keys (sync-committee shape); C3 = aggregate_verify of 128 distinct 32-byte messages (129-pair Miller
+    loop).  Each also with one tampered input: reject, and the (non-trivial) GT still equals the oracle's."""
+    from oracle import c_oracle
+    rnd = random.Random(2024)
+    one = O.f12_to_bytes(O.F12_ONE)
+    # C1 (M/README.md:49, secret key of M/src/signature.rs:105-108 replaced by a seeded one: the oracle pins the value)
+    sk = rnd.randrange(1, O.r)
+    pk = eng.g1_mul_gen([sk])[0].tobytes()
+    sig = eng.g2_mul(eng.hash_to_g2([b"cats"]).reshape(-1), [sk])[0].tobytes()
+    for m in (b"cats", b"dogs"):
+        ok, gt = eng.verify(sig, pk, m, want_gt=True)
+        ok_c, gt_c = c_oracle.fast_aggregate_verify(sig, pk, m, reject_inf=False)
+        assert ok == ok_c == (m == b"cats") and gt == gt_c and (gt == one) == ok
+    # C2
+    n = 512
+    sks = [rnd.randrange(1, O.r) for _ in range(n)]
+    pks = eng.g1_mul_gen(sks)
+    msg = rnd.getrandbits(256).to_bytes(32, "big")
+    sig = eng.g2_mul(eng.hash_to_g2([msg]).reshape(-1), [sum(sks) % O.r])[0].tobytes()
+    ok, gt = eng.fast_aggregate_verify(sig, pks.reshape(-1), msg, want_gt=True)
+    ok_c, gt_c = c_oracle.fast_aggregate_verify(sig, pks.reshape(-1), msg)
+    assert ok and ok_c and gt == gt_c == one
+    ok, gt = eng.fast_aggregate_verify(sig, pks[:-1].reshape(-1), msg, want_gt=True)          # one key missing
+    ok_c, gt_c = c_oracle.fast_aggregate_verify(sig, pks[:-1].reshape(-1), msg)
+    assert not ok and not ok_c and gt == gt_c != one
+    # C3
+    n = 128
+    msgs = [rnd.getrandbits(256).to_bytes(32, "big") for _ in range(n)]
+    H = eng.hash_to_g2(msgs)
+    parts = eng.g2_mul(H.reshape(-1), sks[:n])
+    agg, st = eng.g2_aggregate(parts.reshape(-1), [0, n])
+    assert not st.any()
+    ok, gt = eng.aggregate_verify(agg.tobytes(), pks[:n].reshape(-1), msgs, want_gt=True)
+    ok_c, gt_c = c_oracle.aggregate_verify(agg.tobytes(), pks[:n].reshape(-1), msgs)
+    assert ok and ok_c and gt == gt_c == one
+    swapped = list(msgs); swapped[3], swapped[77] = swapped[77], swapped[3]
+    ok, gt = eng.aggregate_verify(agg.tobytes(), pks[:n].reshape(-1), swapped, want_gt=True)
+    ok_c, gt_c = c_oracle.aggregate_verify(agg.tobytes(), pks[:n].reshape(-1), swapped)
+    assert not ok and not ok_c and gt == gt_c != one
+
+
 def _make_sets(n_sets, n_keys, seed=0):
     sets_o = []
     for j in range(n_sets):
