@@ -47,9 +47,9 @@ FP_MULS = {"g1_aggregate": 1400, "g2_parse_subgroup_check": 1170, "hash_to_g2_af
 FP_MULS_PER_SET = 16400
 # what this implementation actually executes per set (inversion-free maps, bucket-method sum, split
 # Miller loop), in the same unit -- reported beside the SURVEY figure so the fraction cannot flatter the kernels
-EXEC_FP_MULS_PER_SET = 13200
-# DRAM bytes (read + write) per launch at the C4 shape from the committed `ncu --set full` captures (profiles/r1s_h2c_full.txt, r1q_accum_full.txt)
-NCU_TRAFFIC_BYTES = {"hash_to_g2_affine": 534016 + 6311424, "miller_accumulate": 162113792 + 4973056}
+EXEC_FP_MULS_PER_SET = 12900
+# DRAM bytes (read + write) per launch at the C4 shape from the committed `ncu --set full` captures (profiles/r1s_h2c_full.txt, r1t_accum_full.txt)
+NCU_TRAFFIC_BYTES = {"hash_to_g2_affine": 534016 + 6311424, "miller_accumulate": 162358272 + 5568000}
 CPU_PASSES = 4                # timed passes of the CPU baseline over its 2048-set sample (~10 s of CPU work per 4 cores)
 B3_EXTRA_PAIRS = 8            # window sums of the bucket-method signature sum, each its own pair
 BYTES_PER_SET = KEYS_PER_SET * 96 + 192 + MSG_LEN + 8          # algorithmic HBM bytes read per set

@@ -320,19 +320,19 @@ B3_FN_NOINLINE void fp_dot6(fp& r, fp_dot6_args q) {
 }
 
 #if !defined(B3_HOSTSIM)
-// Register-resident variant for the group-cooperative Miller accumulation (kernels.cuh, k_miller_accum): the six `a`
-// operands are the caller's registers (Fp12 coefficients gathered by warp shuffles), the six `b` operands are read from
-// shared memory four limbs at a time (LDS.128).  Same accumulator shapes and bounds as fp_dot6.
+// Register-resident dot product for the group-cooperative Miller accumulation (kernels.cuh, k_miller_accum): the `a`
+// operands are the caller's registers (Fp12 coefficients gathered by warp shuffles), the `b` operands are read from shared
+// memory four limbs at a time (LDS.128).  Same accumulator shapes and bounds as fp_dot6.
 __device__ __forceinline__ uint32_t b3_u4_get(const uint4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
-__device__ __forceinline__ void fp_dot6_rs(fp& r, const fp (&a)[6], const fp* b0, const fp* b1, const fp* b2, const fp* b3,
-                                           const fp* b4, const fp* b5) {
+// Three terms, for the Karatsuba form of the sparse line product: 3 x 144 + 156 multiply-accumulates.
+__device__ __forceinline__ void fp_dot3_rs(fp& r, const fp& a0, const fp& a1, const fp& a2, const fp* b0, const fp* b1, const fp* b2) {
     uint32_t even[12], odd[12];
-    const fp* bp[6] = {b0, b1, b2, b3, b4, b5};
+    const fp* bp[3] = {b0, b1, b2};
 #pragma unroll
     for (int q4 = 0; q4 < 3; q4++) {
-        uint4 bw[6];
+        uint4 bw[3];
 #pragma unroll
-        for (int t = 0; t < 6; t++) bw[t] = reinterpret_cast<const uint4*>(bp[t]->l)[q4];
+        for (int t = 0; t < 3; t++) bw[t] = reinterpret_cast<const uint4*>(bp[t]->l)[q4];
 #pragma unroll
         for (int ii = 0; ii < 4; ii++) {
             const int i = 4 * q4 + ii;
@@ -340,21 +340,22 @@ __device__ __forceinline__ void fp_dot6_rs(fp& r, const fp (&a)[6], const fp* b0
             uint32_t* O = (i & 1) ? even : odd;
             uint32_t bi = b3_u4_get(bw[0], ii);
             if (i == 0) {
-                b3_mul_row(O, a[0].l + 1, bi);
-                b3_mul_row(E, a[0].l, bi);
+                b3_mul_row(O, a0.l + 1, bi);
+                b3_mul_row(E, a0.l, bi);
             } else {
                 E[0] = add_cc(E[0], O[1]);
-                b3_mad_row_shift(O, a[0].l + 1, bi);
-                b3_mad_row(E, a[0].l, bi);
+                b3_mad_row_shift(O, a0.l + 1, bi);
+                b3_mad_row(E, a0.l, bi);
                 O[11] = addc(O[11], 0);
             }
-#pragma unroll
-            for (int t = 1; t < 6; t++) {
-                bi = b3_u4_get(bw[t], ii);
-                b3_mad_row(O, a[t].l + 1, bi);
-                b3_mad_row(E, a[t].l, bi);
-                O[11] = addc(O[11], 0);
-            }
+            bi = b3_u4_get(bw[1], ii);
+            b3_mad_row(O, a1.l + 1, bi);
+            b3_mad_row(E, a1.l, bi);
+            O[11] = addc(O[11], 0);
+            bi = b3_u4_get(bw[2], ii);
+            b3_mad_row(O, a2.l + 1, bi);
+            b3_mad_row(E, a2.l, bi);
+            O[11] = addc(O[11], 0);
             uint32_t m = E[0] * FP_PINV32;
             b3_mad_row(O, FP_P.l + 1, m);
             b3_mad_row(E, FP_P.l, m);
