@@ -331,6 +331,17 @@ B3_FN_NOINLINE bool g2_in_subgroup(const jac<F2>& p) {
     g2_psi(ps, p);
     return pt_eq(xp, ps);
 }
+// the same for an affine point: the five additions of the [|x|] ladder are mixed (7M + 4S instead of 11M + 5S)
+template <class F2>
+B3_FN_NOINLINE bool g2_in_subgroup_aff(const aff<F2>& a) {
+    if (a.inf) return true;
+    jac<F2> xp, p, ps;
+    pt_mul_u64_aff(xp, a, B3_X_ABS);
+    pt_neg(xp, xp);
+    pt_from_aff(p, a);
+    g2_psi(ps, p);
+    return pt_eq(xp, ps);
+}
 B3_FN_NOINLINE bool g1_in_subgroup(const g1_jac& p) {
     if (pt_is_inf(p)) return true;
     g1_jac t, ph;

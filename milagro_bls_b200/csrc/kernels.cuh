@@ -52,9 +52,7 @@ __global__ void B3_LBH k_g2_subgroup(const g2_aff* pts, const int32_t* status, s
     if (status[i] == B3_OK) {
         g2h_aff a;
         g2h_load(a, pts[i]);
-        g2h_jac j;
-        pt_from_aff(j, a);
-        good = g2_in_subgroup(j) ? 1 : 0;
+        good = g2_in_subgroup_aff(a) ? 1 : 0;
     }
     if (!pair_odd()) ok[i] = good;
 }

@@ -237,6 +237,7 @@ int hs_g2_check(const uint8_t* a192, int* on_curve, int* in_subgroup) {
     *on_curve = pt_on_curve_aff(A);
     g2_jac P; pt_from_aff(P, A);
     *in_subgroup = g2_in_subgroup(P);
+    if ((g2_in_subgroup_aff(A) ? 1 : 0) != *in_subgroup) return -99;      // the mixed-addition variant must agree
     return 0;
 }
 // GT = fexp( prod_i miller(Q_i, P_i) )
