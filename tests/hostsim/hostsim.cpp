@@ -40,6 +40,10 @@ void hs_fp_mont_mul_raw(const uint8_t* a, const uint8_t* b, uint8_t* out) {
 void hs_fp_sqr_raw(const uint8_t* a, uint8_t* out) {
     fp x, r; fp_raw_from_be(x, a); fp_sqr(r, x); fp_raw_to_be(out, r);
 }
+// a^e for a plain 384-bit exponent e (sliding-window fp_pow_const)
+void hs_fp_pow(const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    fp x, ex, r; fp_in(x, a); fp_raw_from_be(ex, b); fp_pow_const(r, x, ex); fp_out(out, r);
+}
 void hs_fp2_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     fp2 x, y, r;
     fp2_in(x, a); fp2_in(y, b);

@@ -29,6 +29,7 @@ def hs():
 test_fp_ops = T.test_fp_ops
 test_fp_mont_mul_raw_edges = T.test_fp_mont_mul_raw_edges
 test_fp_sqr_raw_limb_patterns = T.test_fp_sqr_raw_limb_patterns
+test_fp_pow_sliding_window = T.test_fp_pow_sliding_window
 test_fp2_ops = T.test_fp2_ops
 test_fp2_sqrt_or_z = T.test_fp2_sqrt_or_z
 test_fp12_ops = T.test_fp12_ops

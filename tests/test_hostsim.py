@@ -102,6 +102,22 @@ def test_fp_sqr_raw_limb_patterns(hs):
         assert int.from_bytes(out.raw, "big") == a * a * Rinv % p, hex(a)
 
 
+def test_fp_pow_sliding_window(hs):
+    """fp_pow_const (5-bit sliding windows over odd powers): exponents around the window boundaries, with long runs of ones
+    and of zeros, the two exponents the path uses, and random ones."""
+    exps = [0, 1, 2, 3, 31, 32, 33, 63, 64, 0b1000001, 0b11111011111, (1 << 383) | 1, (1 << 384) - 1, (1 << 200) - 1,
+            1 << 383, (p - 3) // 4, p - 2, (p - 1) // 2]
+    exps += [rnd.getrandbits(384) for _ in range(6)] + [rnd.getrandbits(70) for _ in range(6)]
+    for e in exps:
+        a = rfp() or 1
+        out = ctypes.create_string_buffer(48)
+        hs.hs_fp_pow(a.to_bytes(48, "big"), e.to_bytes(48, "big"), out)
+        assert int.from_bytes(out.raw, "big") == pow(a, e, p), hex(e)
+    out = ctypes.create_string_buffer(48)
+    hs.hs_fp_pow((0).to_bytes(48, "big"), (5).to_bytes(48, "big"), out)
+    assert int.from_bytes(out.raw, "big") == 0
+
+
 def test_fp2_ops(hs):
     for _ in range(50):
         a, b = rfp2(), rfp2()
