@@ -612,7 +612,7 @@ __global__ void B3_LBH k_miller_lines(const g2_jac* __restrict__ q, size_t n, si
 //    partial[s * chunks + chunk] = product of the CTA's lines.
 #define B3_ACC_GROUPS 20
 // line operands of one group in shared memory: v[0..4] = X.c0, v[5..9] = X.c1, v[10..14] = X.c0 + X.c1 for X = l0, l3, xi l3, l5,
-// xi l5, v[15] = 0, v[16], v[17] = write-only sinks for lanes with nothing to derive
+// xi l5, v[15] = 0 (operand of the lanes with nothing to derive), v[16], v[17] unused
 struct acc_ops {
     fp v[18];
 };
@@ -658,10 +658,10 @@ __global__ void __launch_bounds__(B3_TPB, 3) k_miller_accum(const fp2* __restric
         if (valid) {
             fp t;
             fp_sub(t, o[ksx], o[ksy]);
-            o[ksd] = t;
+            if (k == 2 || k == 3) o[ksd] = t;              // predicated stores: lanes with nothing to derive write nothing
             fp_add(t, o[kau], o[kav]);
-            o[kad] = t;
-            o[kad2] = t;
+            if (k != 5) o[kad] = t;
+            if (k == 2 || k == 3) o[kad2] = t;
         }
         __syncwarp();
         fp as0, as1, as2;                                  // c0 + c1 of this lane's coefficient and of the two gathered ones
