@@ -58,9 +58,13 @@ const char* b3_stage_name(int stage);
 /* serial != 0: run the independent stages of a verification call one after another on the context's stream (for
  * per-stage timing); default 0: they overlap on internal streams, joined before the Miller loop */
 void b3_ctx_set_serial(b3_ctx* ctx, int serial);
-/* finishing kernel of b3_verify_batch: 0 = chosen by batch size (default), 1 = one CTA per item, 2 = one thread per item,
- * 3 = one lane pair per item */
+/* finishing kernel of b3_verify_batch: 0 = chosen by batch size (default), 1 = one CTA per item, 3 = one lane pair per item */
 void b3_ctx_set_item_kernel(b3_ctx* ctx, int which);
+/* The aggregation kernels check that every key / signature they add is ON THE CURVE (the reference's types cannot hold any
+ * other point: every constructor checks, M/src/keys.rs:140-175, M/src/signature.rs:43-46).  trusted != 0 declares that the
+ * point arrays passed to this context come out of this library's own decompress / validate / aggregate calls (the
+ * reference's type invariant) and skips that check.  Default 0. */
+void b3_ctx_set_trusted_points(b3_ctx* ctx, int trusted);
 int b3_stage_count(void);
 
 /* ---- (de)serialisation: PublicKey::{from_bytes, from_bytes_unchecked, as_bytes} (M/src/keys.rs:140-160),
@@ -112,6 +116,43 @@ int b3_verify_multiple(b3_ctx*, const uint8_t* sigs192, const uint8_t* pks96, co
                        const uint8_t* msgs, const uint32_t* msg_off, const uint64_t* scalars, size_t n,
                        int* accept, int64_t* first_bad, uint8_t* gt576);
 
+/* The same in two phases, keeping the reference's RNG contract (M/src/aggregates.rs:272-287: the scalar of set j is drawn only
+ * after signatures 0..j passed subgroup_check_g2; nothing is drawn for or after the first failing set) without any work done
+ * twice.  b3_sig_precheck uploads, parses and subgroup-checks the signatures and returns first_bad (-1: all passed; a malformed
+ * signature returns its AmclError code).  The caller draws min(first_bad, n) scalars; if first_bad < 0 it calls
+ * b3_verify_multiple_checked (or b3_verify_multiple_indexed with sigs192 == NULL) ON THE SAME CONTEXT with the same n, which
+ * reuses the checked signatures.  Any scalar equal to 0 is rejected with B3_ERR_ARG by every verify_multiple entry: the
+ * reference's draw rule never yields it, and it would drop its set from the batch equation. */
+int b3_sig_precheck(b3_ctx*, const uint8_t* sigs192, size_t n, int64_t* first_bad);
+int b3_verify_multiple_checked(b3_ctx*, const uint8_t* pks96, const uint32_t* pk_off, const uint8_t* msgs,
+                               const uint32_t* msg_off, const uint64_t* scalars, size_t n, int* accept, uint8_t* gt576);
+
+/* ---- device-resident public-key table.  PublicKey::from_bytes -- decompression + key_validate,
+ *      M/src/keys.rs:140-147 -- is paid ONCE per validator; verification calls then name keys by u32 index: 4 bytes instead of
+ *      96 per key over PCIe, and no parsing, Montgomery conversion or curve check per use.  A table belongs to the device of
+ *      the context that created it and is read-only during verification: any number of contexts may share it.
+ *      b3_keytable_append: compressed != 0 -> 48-byte ZCash-compressed keys (PublicKey::from_bytes; validate = 0 gives
+ *      from_bytes_unchecked), else 96-byte uncompressed (from_uncompressed_bytes, on-curve check always).  status[i]
+ *      (nullable) = B3_OK or the AmclError code; a rejected key keeps its slot, marked invalid -- every set naming it fails
+ *      with B3_ERR_INVALID_POINT -- so indices stay aligned with the caller's numbering.  first_index (nullable) receives
+ *      the index of keys[0].  Not thread-safe against concurrent verification calls when it has to grow. ---- */
+typedef struct b3_keytable b3_keytable;
+int b3_keytable_create(b3_ctx*, size_t capacity, b3_keytable** out);
+void b3_keytable_destroy(b3_keytable*);
+size_t b3_keytable_size(const b3_keytable*);
+int b3_keytable_append(b3_ctx*, b3_keytable*, const uint8_t* keys, size_t n, int compressed, int validate,
+                       int32_t* status, size_t* first_index);
+/* entries idx[0..n) back as 96-byte uncompressed keys (PublicKey::as_uncompressed_bytes, M/src/keys.rs:163-165) */
+int b3_keytable_get(b3_ctx*, const b3_keytable*, const uint32_t* idx, size_t n, uint8_t* out96, int32_t* status);
+/* AggregatePublicKey::into_aggregate (M/src/aggregates.rs:46-56) over table indices: set s = key_idx[off[s] .. off[s+1]) */
+int b3_g1_aggregate_indexed(b3_ctx*, const b3_keytable*, const uint32_t* key_idx, const uint32_t* off, size_t n_sets,
+                            uint8_t* out96, int32_t* status);
+/* b3_verify_multiple with the keys of set j = table entries key_idx[pk_off[j] .. pk_off[j+1]) (pk_off == NULL: one entry per
+ * set).  sigs192 == NULL: the signatures of the preceding b3_sig_precheck on this context. */
+int b3_verify_multiple_indexed(b3_ctx*, const b3_keytable*, const uint8_t* sigs192, const uint32_t* key_idx,
+                               const uint32_t* pk_off, const uint8_t* msgs, const uint32_t* msg_off,
+                               const uint64_t* scalars, size_t n, int* accept, int64_t* first_bad, uint8_t* gt576);
+
 /* ---- batched verification of n INDEPENDENT items with one accept bit each (locating the bad set
  *      after a batch reject, or bulk verification of unrelated signatures).  Item i is, by `mode`,
  *        B3_ITEM_VERIFY          Signature::verify(sig_i, msg_i, pk_i)                           (M/src/signature.rs:27-40)
@@ -142,6 +183,14 @@ int b3_verify_multiple_partial_dev(b3_ctx*, const uint8_t* sigs192_dev, const ui
 int b3_verify_multiple_partial(b3_ctx*, const uint8_t* sigs192, const uint8_t* pks96, const uint32_t* pk_off,
                                const uint8_t* msgs, const uint32_t* msg_off, const uint64_t* scalars, size_t n,
                                int64_t index_base, uint8_t* partial_dev);
+/* the two partial forms over a key table */
+int b3_verify_multiple_indexed_partial(b3_ctx*, const b3_keytable*, const uint8_t* sigs192, const uint32_t* key_idx,
+                                       const uint32_t* pk_off, const uint8_t* msgs, const uint32_t* msg_off,
+                                       const uint64_t* scalars, size_t n, int64_t index_base, uint8_t* partial_dev);
+int b3_verify_multiple_indexed_partial_dev(b3_ctx*, const b3_keytable*, const uint8_t* sigs192_dev,
+                                           const uint32_t* key_idx_dev, const uint32_t* pk_off_dev, const uint8_t* msgs_dev,
+                                           const uint32_t* msg_off_dev, const uint64_t* scalars_dev, size_t n,
+                                           int64_t index_base, uint8_t* partial_dev);
 /* product of n_partials partials (gathered from all ranks) -> one final exponentiation -> accept, first_bad, gt */
 int b3_combine_partials_dev(b3_ctx*, const uint8_t* partials_dev, size_t n_partials, int* accept, int64_t* first_bad,
                             uint8_t* gt576);
@@ -151,6 +200,34 @@ int b3_verify_batch_dev(b3_ctx*, int mode, const uint8_t* sigs192_dev, const uin
 int b3_hash_to_g2_dev(b3_ctx*, const uint8_t* msgs_dev, const uint32_t* off_dev, size_t n, uint8_t* out192_dev);
 int b3_g1_aggregate_dev(b3_ctx*, const uint8_t* pks96_dev, const uint32_t* off_dev, size_t n_sets, uint8_t* out96_dev,
                         int32_t* status_dev);
+
+/* ---- multi-GPU: the sharded form of verify_multiple_aggregate_signatures (M/src/aggregates.rs:261-316).
+ *      One process per GPU.  Rank r verifies sets [index_base, index_base + n) of the global batch (scalars drawn for the
+ *      GLOBAL set order); the 592-byte partials are combined with ONE ncclAllGather over NVLink / NVSwitch and one final
+ *      exponentiation on every rank, so every rank returns the global accept bit, the global first_bad and the GT of the whole
+ *      batch.  NCCL is bound at run time (the libnccl.so.2 already in the process, else the system one, or $B3_NCCL_LIB).
+ *      b3_nccl_unique_id: call on one rank, ship the 128 bytes to the others by any means (the Rust host's own transport).
+ *      A communicator serves `lanes` contexts of this process (one host thread + b3_ctx each); call k of lane t is step k,
+ *      and the all-gather of a step carries the partials of all its lanes (issued by the lane that deposits last, on the
+ *      communicator's own high-priority stream).  Every rank must use the same `lanes` and make the same calls per lane.
+ *      b3_sharded_begin returns once this rank's partial is deposited; b3_sharded_finish combines.  A lane may begin step
+ *      k + 1 before finishing step k (at most 3 steps open), which gives the collective a whole call time to complete.
+ *      keys = pks96 (table == NULL) or u32 indices into `table`; device_pointers != 0: all input pointers are device memory. ---- */
+typedef struct b3_comm b3_comm;
+int b3_nccl_unique_id(uint8_t id128[128]);
+int b3_comm_create(int device, int nranks, int rank, const uint8_t id128[128], int lanes, b3_comm** out);
+void b3_comm_destroy(b3_comm*);
+const char* b3_comm_last_error(b3_comm*);
+/* number of collectives issued so far (one per step) */
+uint64_t b3_comm_collective_count(b3_comm*);
+int b3_sharded_begin(b3_ctx*, b3_comm*, int lane, const b3_keytable* table, const uint8_t* sigs192, const void* keys,
+                     const uint32_t* pk_off, const uint8_t* msgs, const uint32_t* msg_off, const uint64_t* scalars, size_t n,
+                     int64_t index_base, int device_pointers, int64_t* ticket);
+int b3_sharded_finish(b3_ctx*, b3_comm*, int lane, int64_t ticket, int* accept, int64_t* first_bad, uint8_t* gt576);
+int b3_verify_multiple_sharded(b3_ctx*, b3_comm*, int lane, const b3_keytable* table, const uint8_t* sigs192,
+                               const void* keys, const uint32_t* pk_off, const uint8_t* msgs, const uint32_t* msg_off,
+                               const uint64_t* scalars, size_t n, int64_t index_base, int device_pointers, int* accept,
+                               int64_t* first_bad, uint8_t* gt576);
 
 /* ---- signing-side helpers.  OUT of the verification path (the reference's Signature::new / SecretKey live on
  *      the CPU); exported only so tests and bench.py can synthesise valid inputs at full size quickly.

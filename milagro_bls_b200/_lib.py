@@ -49,6 +49,7 @@ def lib():
         "b3_stage_count": ([], ctypes.c_int),
         "b3_ctx_set_serial": ([vp, ctypes.c_int], None),
         "b3_ctx_set_item_kernel": ([vp, ctypes.c_int], None),
+        "b3_ctx_set_trusted_points": ([vp, ctypes.c_int], None),
         "b3_g1_decompress": ([vp, u8p, sz, ctypes.c_int, u8p, i32p], ctypes.c_int),
         "b3_g2_decompress": ([vp, u8p, sz, u8p, i32p], ctypes.c_int),
         "b3_g1_compress": ([vp, u8p, sz, u8p, i32p], ctypes.c_int),
@@ -63,6 +64,26 @@ def lib():
         "b3_fast_aggregate_verify_pre_aggregated": ([vp, u8p, u8p, u8p, sz, ip, u8p], ctypes.c_int),
         "b3_aggregate_verify": ([vp, u8p, u8p, u8p, vp, sz, ip, u8p], ctypes.c_int),
         "b3_verify_multiple": ([vp, u8p, u8p, vp, u8p, vp, vp, sz, ip, i64p, u8p], ctypes.c_int),
+        "b3_sig_precheck": ([vp, u8p, sz, i64p], ctypes.c_int),
+        "b3_verify_multiple_checked": ([vp, u8p, vp, u8p, vp, vp, sz, ip, u8p], ctypes.c_int),
+        "b3_keytable_create": ([vp, sz, ctypes.POINTER(vp)], ctypes.c_int),
+        "b3_keytable_destroy": ([vp], None),
+        "b3_keytable_size": ([vp], sz),
+        "b3_keytable_append": ([vp, vp, u8p, sz, ctypes.c_int, ctypes.c_int, i32p, ctypes.POINTER(sz)], ctypes.c_int),
+        "b3_keytable_get": ([vp, vp, vp, sz, u8p, i32p], ctypes.c_int),
+        "b3_g1_aggregate_indexed": ([vp, vp, vp, vp, sz, u8p, i32p], ctypes.c_int),
+        "b3_verify_multiple_indexed": ([vp, vp, u8p, vp, vp, u8p, vp, vp, sz, ip, i64p, u8p], ctypes.c_int),
+        "b3_verify_multiple_indexed_partial": ([vp, vp, u8p, vp, vp, u8p, vp, vp, sz, ctypes.c_int64, vp], ctypes.c_int),
+        "b3_verify_multiple_indexed_partial_dev": ([vp, vp, vp, vp, vp, vp, vp, vp, sz, ctypes.c_int64, vp], ctypes.c_int),
+        "b3_nccl_unique_id": ([u8p], ctypes.c_int),
+        "b3_comm_create": ([ctypes.c_int, ctypes.c_int, ctypes.c_int, u8p, ctypes.c_int, ctypes.POINTER(vp)], ctypes.c_int),
+        "b3_comm_destroy": ([vp], None),
+        "b3_comm_last_error": ([vp], ctypes.c_char_p),
+        "b3_comm_collective_count": ([vp], ctypes.c_uint64),
+        "b3_sharded_begin": ([vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, sz, ctypes.c_int64, ctypes.c_int, i64p], ctypes.c_int),
+        "b3_sharded_finish": ([vp, vp, ctypes.c_int, ctypes.c_int64, ip, i64p, u8p], ctypes.c_int),
+        "b3_verify_multiple_sharded": ([vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, sz, ctypes.c_int64, ctypes.c_int, ip, i64p, u8p],
+                                       ctypes.c_int),
         "b3_verify_batch": ([vp, ctypes.c_int, u8p, u8p, vp, u8p, vp, sz, i32p, i32p, u8p], ctypes.c_int),
         "b3_verify_batch_dev": ([vp, ctypes.c_int, vp, vp, vp, vp, vp, sz, vp, vp, vp], ctypes.c_int),
         "b3_verify_multiple_partial_dev": ([vp, vp, vp, vp, vp, vp, vp, sz, ctypes.c_int64, vp], ctypes.c_int),
@@ -83,13 +104,11 @@ def lib():
     return L
 
 
-EXPORTED_SYMBOLS = [
-    "b3_ctx_create", "b3_ctx_destroy", "b3_last_error", "b3_ctx_stream", "b3_ctx_launch_count", "b3_ctx_last_kernel_ms",
-    "b3_ctx_stage_ms", "b3_stage_name", "b3_stage_count", "b3_ctx_set_serial", "b3_ctx_set_item_kernel",
-    "b3_g1_decompress", "b3_g2_decompress", "b3_g1_compress", "b3_g2_compress", "b3_g1_validate", "b3_g2_subgroup_check",
-    "b3_g1_aggregate", "b3_g2_aggregate", "b3_hash_to_g2", "b3_verify", "b3_fast_aggregate_verify",
-    "b3_fast_aggregate_verify_pre_aggregated", "b3_aggregate_verify", "b3_verify_multiple",
-    "b3_verify_batch", "b3_verify_batch_dev",
-    "b3_verify_multiple_partial_dev", "b3_verify_multiple_partial", "b3_combine_partials_dev", "b3_hash_to_g2_dev", "b3_g1_aggregate_dev",
-    "b3_g1_mul_gen", "b3_g2_mul", "b3_imad_peak",
-]
+def _symbols_of_table():
+    """Names bound above, read from this file's own source (so the list cannot drift from the table)."""
+    import re
+    src = open(os.path.abspath(__file__).replace(".pyc", ".py")).read()
+    return sorted(set(re.findall(r'^        "(b3_[a-z0-9_]+)": \(', src, flags=re.M)))
+
+
+EXPORTED_SYMBOLS = _symbols_of_table()

@@ -48,6 +48,16 @@ def _buf(b):
     return ctypes.c_void_p(a.ctypes.data), a
 
 
+def _need(cond, what):
+    """Argument validation before anything reaches the C side (which trusts its sizes)."""
+    if not cond:
+        raise ValueError(f"milagro_bls_b200: {what}")
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
 def _offsets(chunks):
     off = np.zeros(len(chunks) + 1, dtype=np.uint32)
     if len(chunks):
@@ -97,7 +107,7 @@ class Engine:
         self.L.b3_ctx_set_serial(self.handle, 1 if serial else 0)
 
     def set_item_kernel(self, which=0):
-        """Finishing kernel of verify_batch: 0 = by batch size, 1 = CTA per item, 2 = thread per item, 3 = lane pair per item."""
+        """Finishing kernel of verify_batch: 0 = by batch size, 1 = CTA per item, 3 = lane pair per item."""
         self.L.b3_ctx_set_item_kernel(self.handle, int(which))
 
     def stage_ms(self):
@@ -158,6 +168,8 @@ class Engine:
     def g1_aggregate(self, pks96, offsets):
         off = np.ascontiguousarray(offsets, dtype=np.uint32)
         n = len(off) - 1
+        _need(n >= 0 and (n == 0 or (off[0] == 0 and int(off[-1]) * 96 == len(pks96) and np.all(np.diff(off.astype(np.int64)) >= 0))),
+              "g1_aggregate: offsets must start at 0, be non-decreasing and end at len(pks96) / 96")
         p, keep = _buf(pks96)
         out = np.zeros(96 * max(n, 1), dtype=np.uint8)
         st = np.zeros(max(n, 1), dtype=np.int32)
@@ -168,6 +180,8 @@ class Engine:
     def g2_aggregate(self, sigs192, offsets):
         off = np.ascontiguousarray(offsets, dtype=np.uint32)
         n = len(off) - 1
+        _need(n >= 0 and (n == 0 or (off[0] == 0 and int(off[-1]) * 192 == len(sigs192) and np.all(np.diff(off.astype(np.int64)) >= 0))),
+              "g2_aggregate: offsets must start at 0, be non-decreasing and end at len(sigs192) / 192")
         p, keep = _buf(sigs192)
         out = np.zeros(192 * max(n, 1), dtype=np.uint8)
         st = np.zeros(max(n, 1), dtype=np.int32)
@@ -190,6 +204,7 @@ class Engine:
         return out[:192 * n].reshape(n, 192)
 
     def verify(self, sig192, pk96, msg, want_gt=False):
+        _need(len(sig192) == 192 and len(pk96) == 96, "verify: signature must be 192 bytes and the key 96 bytes (uncompressed)")
         ok = ctypes.c_int(0)
         gt = np.zeros(576, dtype=np.uint8)
         ps, k1 = _buf(sig192)
@@ -199,6 +214,7 @@ class Engine:
         return (bool(ok.value), gt.tobytes()) if want_gt else bool(ok.value)
 
     def fast_aggregate_verify(self, sig192, pks96, msg, want_gt=False):
+        _need(len(sig192) == 192 and len(pks96) % 96 == 0, "fast_aggregate_verify: 192-byte signature, keys a multiple of 96 bytes")
         ok = ctypes.c_int(0)
         gt = np.zeros(576, dtype=np.uint8)
         ps, k1 = _buf(sig192)
@@ -208,6 +224,7 @@ class Engine:
         return (bool(ok.value), gt.tobytes()) if want_gt else bool(ok.value)
 
     def fast_aggregate_verify_pre_aggregated(self, sig192, apk96, msg, want_gt=False):
+        _need(len(sig192) == 192 and len(apk96) == 96, "fast_aggregate_verify_pre_aggregated: 192-byte signature, 96-byte key")
         ok = ctypes.c_int(0)
         gt = np.zeros(576, dtype=np.uint8)
         ps, k1 = _buf(sig192)
@@ -220,6 +237,7 @@ class Engine:
         ok = ctypes.c_int(0)
         gt = np.zeros(576, dtype=np.uint8)
         n = len(msgs)
+        _need(len(sig192) == 192 and len(pks96) == 96 * n, "aggregate_verify: 192-byte signature and one 96-byte key per message")
         off = _offsets(msgs)
         ps, k1 = _buf(sig192)
         pp, k2 = _buf(pks96)
@@ -227,32 +245,102 @@ class Engine:
         self._ck(self.L.b3_aggregate_verify(self.handle, ps, pp, pm, off.ctypes.data, n, ctypes.byref(ok), gt.ctypes.data))
         return (bool(ok.value), gt.tobytes()) if want_gt else bool(ok.value)
 
+    def _vm_args(self, sigs192, keys, key_bytes, pk_offsets, msgs_blob, msg_offsets, scalars, what):
+        """Validated, contiguous arguments of a verify_multiple-shaped call.  keys: bytes / uint8 array of 96-byte records
+        (key_bytes = 96) or an array of u32 table indices (key_bytes = 4)."""
+        sc = np.ascontiguousarray(scalars, dtype=np.uint64)
+        n = len(sc)
+        moff = _u32(msg_offsets)
+        _need(len(moff) == n + 1 and (n == 0 or moff[0] == 0) and int(moff[-1]) == len(msgs_blob), f"{what}: message offsets must be n + 1 values ending at len(msgs)")
+        _need(sigs192 is None or len(sigs192) == 192 * n, f"{what}: one 192-byte signature per set")
+        if key_bytes == 4:
+            kk = _u32(keys)
+            nk = len(kk)
+            pp, k2 = ctypes.c_void_p(kk.ctypes.data), kk
+        else:
+            _need(len(keys) % 96 == 0, f"{what}: keys must be 96-byte records")
+            nk = len(keys) // 96
+            pp, k2 = _buf(keys)
+        if pk_offsets is None:
+            _need(nk == n, f"{what}: one key per set when pk_offsets is None")
+            koff, po = None, None
+        else:
+            koff = _u32(pk_offsets)
+            _need(len(koff) == n + 1 and (n == 0 or koff[0] == 0) and int(koff[-1]) == nk and np.all(np.diff(koff.astype(np.int64)) >= 0),
+                  f"{what}: key offsets must be n + 1 non-decreasing values ending at the number of keys")
+            po = koff.ctypes.data
+        ps, k1 = (None, None) if sigs192 is None else _buf(sigs192)
+        pm, k3 = _buf(msgs_blob)
+        return n, ps, pp, po, pm, moff, sc, (k1, k2, k3, koff)
+
     def verify_multiple(self, sigs192, pks96, pk_offsets, msgs_blob, msg_offsets, scalars, want_gt=False):
         """Raw batched form of verify_multiple_aggregate_signatures.  pk_offsets None -> pks96 holds one
         (aggregate) key per set.  Returns (accept, first_bad[, gt])."""
-        sc = np.ascontiguousarray(scalars, dtype=np.uint64)
-        n = len(sc)
-        moff = np.ascontiguousarray(msg_offsets, dtype=np.uint32)
+        n, ps, pp, po, pm, moff, sc, keep = self._vm_args(sigs192, pks96, 96, pk_offsets, msgs_blob, msg_offsets, scalars, "verify_multiple")
         ok = ctypes.c_int(0)
         fb = ctypes.c_int64(-1)
         gt = np.zeros(576, dtype=np.uint8)
-        ps, k1 = _buf(sigs192)
-        pp, k2 = _buf(pks96)
-        pm, k3 = _buf(msgs_blob)
-        if pk_offsets is None:
-            po = None
-        else:
-            koff = np.ascontiguousarray(pk_offsets, dtype=np.uint32)
-            po = koff.ctypes.data
         self._ck(self.L.b3_verify_multiple(self.handle, ps, pp, po, pm, moff.ctypes.data, sc.ctypes.data, n,
                                            ctypes.byref(ok), ctypes.byref(fb), gt.ctypes.data))
         return (bool(ok.value), int(fb.value), gt.tobytes()) if want_gt else (bool(ok.value), int(fb.value))
+
+    def sig_precheck(self, sigs192):
+        """Phase one of the two-phase call: upload, parse and subgroup-check the signatures; returns first_bad (-1: all passed).
+        The checked signatures stay in this context for verify_multiple_checked / verify_multiple_indexed(sigs192=None)."""
+        _need(len(sigs192) % 192 == 0, "sig_precheck: signatures must be 192-byte records")
+        fb = ctypes.c_int64(-1)
+        ps, k1 = _buf(sigs192)
+        self._ck(self.L.b3_sig_precheck(self.handle, ps, len(sigs192) // 192, ctypes.byref(fb)))
+        return int(fb.value)
+
+    def verify_multiple_checked(self, pks96, pk_offsets, msgs_blob, msg_offsets, scalars, want_gt=False):
+        """Phase two: the batch equation over the signatures of the preceding sig_precheck.  Returns accept[, gt]."""
+        n, ps, pp, po, pm, moff, sc, keep = self._vm_args(None, pks96, 96, pk_offsets, msgs_blob, msg_offsets, scalars, "verify_multiple_checked")
+        ok = ctypes.c_int(0)
+        gt = np.zeros(576, dtype=np.uint8)
+        self._ck(self.L.b3_verify_multiple_checked(self.handle, pp, po, pm, moff.ctypes.data, sc.ctypes.data, n, ctypes.byref(ok), gt.ctypes.data))
+        return (bool(ok.value), gt.tobytes()) if want_gt else bool(ok.value)
+
+    def verify_multiple_indexed(self, table, sigs192, key_idx, pk_offsets, msgs_blob, msg_offsets, scalars, want_gt=False):
+        """verify_multiple with the keys named by u32 indices into a KeyTable.  sigs192 None -> the signatures of the
+        preceding sig_precheck.  Returns (accept, first_bad[, gt])."""
+        n, ps, pp, po, pm, moff, sc, keep = self._vm_args(sigs192, key_idx, 4, pk_offsets, msgs_blob, msg_offsets, scalars, "verify_multiple_indexed")
+        ok = ctypes.c_int(0)
+        fb = ctypes.c_int64(-1)
+        gt = np.zeros(576, dtype=np.uint8)
+        self._ck(self.L.b3_verify_multiple_indexed(self.handle, table.handle, ps, pp, po, pm, moff.ctypes.data, sc.ctypes.data, n,
+                                                   ctypes.byref(ok), ctypes.byref(fb), gt.ctypes.data))
+        return (bool(ok.value), int(fb.value), gt.tobytes()) if want_gt else (bool(ok.value), int(fb.value))
+
+    def g1_aggregate_indexed(self, table, key_idx, offsets):
+        off = _u32(offsets)
+        kk = _u32(key_idx)
+        n = len(off) - 1
+        _need(n >= 0 and (n == 0 or (off[0] == 0 and int(off[-1]) == len(kk) and np.all(np.diff(off.astype(np.int64)) >= 0))),
+              "g1_aggregate_indexed: offsets must start at 0, be non-decreasing and end at len(key_idx)")
+        out = np.zeros(96 * max(n, 1), dtype=np.uint8)
+        st = np.zeros(max(n, 1), dtype=np.int32)
+        self._ck(self.L.b3_g1_aggregate_indexed(self.handle, table.handle, kk.ctypes.data, off.ctypes.data, n, out.ctypes.data,
+                                                st.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        return out[:96 * n], st[:n]
+
+    def set_trusted_points(self, trusted=True):
+        """trusted=True: the point arrays passed to this context come out of this library's own decompress / validate calls
+        (the reference's type invariant), so the aggregation kernels skip their on-curve checks."""
+        self.L.b3_ctx_set_trusted_points(self.handle, 1 if trusted else 0)
 
     def verify_batch(self, mode, sigs192, pks96, pk_offsets, msgs, want_gt=False):
         """n independent items, one accept bit each (b3_verify_batch).  mode: _lib.ITEM_VERIFY (one key per item),
         ITEM_FAST_AGGREGATE (keys of item i = pks96[pk_offsets[i]:pk_offsets[i+1]]), ITEM_PRE_AGGREGATED.
         msgs: list of byte strings.  Returns (accept[n] bool array, status[n] int32 array[, gt (n, 576) uint8])."""
         n = len(msgs)
+        _need(len(sigs192) == 192 * n and len(pks96) % 96 == 0, "verify_batch: one 192-byte signature per item, keys in 96-byte records")
+        if pk_offsets is None:
+            _need(len(pks96) == 96 * n, "verify_batch: one key per item when pk_offsets is None")
+        else:
+            ko = _u32(pk_offsets)
+            _need(len(ko) == n + 1 and (n == 0 or ko[0] == 0) and int(ko[-1]) * 96 == len(pks96) and np.all(np.diff(ko.astype(np.int64)) >= 0),
+                  "verify_batch: key offsets must be n + 1 non-decreasing values ending at the number of keys")
         accept = np.zeros(max(n, 1), dtype=np.int32)
         status = np.zeros(max(n, 1), dtype=np.int32)
         gt = np.zeros((max(n, 1), 576), dtype=np.uint8) if want_gt else None
@@ -281,14 +369,42 @@ class Engine:
 
     def verify_multiple_partial(self, sigs192, pks96, pk_offsets, msgs_blob, msg_offsets, scalars, index_base, d_partial):
         """This rank's shard from HOST buffers -> 592-byte partial in device memory at d_partial (b3_verify_multiple_partial)."""
-        sc = np.ascontiguousarray(scalars, dtype=np.uint64)
-        moff = np.ascontiguousarray(msg_offsets, dtype=np.uint32)
-        ps, k1 = _buf(sigs192)
-        pp, k2 = _buf(pks96)
-        pm, k3 = _buf(msgs_blob)
-        po = None if pk_offsets is None else np.ascontiguousarray(pk_offsets, dtype=np.uint32)
-        self._ck(self.L.b3_verify_multiple_partial(self.handle, ps, pp, None if po is None else po.ctypes.data, pm, moff.ctypes.data,
-                                                   sc.ctypes.data, len(sc), index_base, d_partial))
+        n, ps, pp, po, pm, moff, sc, keep = self._vm_args(sigs192, pks96, 96, pk_offsets, msgs_blob, msg_offsets, scalars, "verify_multiple_partial")
+        self._ck(self.L.b3_verify_multiple_partial(self.handle, ps, pp, po, pm, moff.ctypes.data, sc.ctypes.data, n, index_base, d_partial))
+
+    def verify_multiple_indexed_partial(self, table, sigs192, key_idx, pk_offsets, msgs_blob, msg_offsets, scalars, index_base, d_partial):
+        n, ps, pp, po, pm, moff, sc, keep = self._vm_args(sigs192, key_idx, 4, pk_offsets, msgs_blob, msg_offsets, scalars,
+                                                          "verify_multiple_indexed_partial")
+        self._ck(self.L.b3_verify_multiple_indexed_partial(self.handle, table.handle, ps, pp, po, pm, moff.ctypes.data, sc.ctypes.data, n,
+                                                           index_base, d_partial))
+
+    def verify_multiple_indexed_partial_dev(self, table, d_sigs, d_idx, d_pk_off, d_msgs, d_msg_off, d_scalars, n, index_base, d_partial):
+        self._ck(self.L.b3_verify_multiple_indexed_partial_dev(self.handle, table.handle, d_sigs, d_idx, d_pk_off, d_msgs, d_msg_off, d_scalars, n,
+                                                               index_base, d_partial))
+
+    # ---- multi-GPU (b3_comm_*: NCCL behind the C ABI) ---------------------------------------------------------
+    def sharded_begin(self, comm, lane, table, sigs192, keys, pk_offsets, msgs_blob, msg_offsets, scalars, index_base):
+        """This rank's shard (HOST buffers) -> partial, deposited for the step's all-gather.  keys: 96-byte records (table None) or
+        u32 table indices.  Returns the ticket for sharded_finish."""
+        n, ps, pp, po, pm, moff, sc, keep = self._vm_args(sigs192, keys, 96 if table is None else 4, pk_offsets, msgs_blob, msg_offsets, scalars,
+                                                          "sharded_begin")
+        t = ctypes.c_int64(-1)
+        self._ck(self.L.b3_sharded_begin(self.handle, comm.handle, lane, None if table is None else table.handle, ps, pp, po, pm,
+                                         moff.ctypes.data, sc.ctypes.data, n, index_base, 0, ctypes.byref(t)))
+        return int(t.value)
+
+    def sharded_begin_dev(self, comm, lane, table, d_sigs, d_keys, d_pk_off, d_msgs, d_msg_off, d_scalars, n, index_base):
+        t = ctypes.c_int64(-1)
+        self._ck(self.L.b3_sharded_begin(self.handle, comm.handle, lane, None if table is None else table.handle, d_sigs, d_keys, d_pk_off,
+                                         d_msgs, d_msg_off, d_scalars, n, index_base, 1, ctypes.byref(t)))
+        return int(t.value)
+
+    def sharded_finish(self, comm, lane, ticket, want_gt=False):
+        ok = ctypes.c_int(0)
+        fb = ctypes.c_int64(-1)
+        gt = np.zeros(576, dtype=np.uint8)
+        self._ck(self.L.b3_sharded_finish(self.handle, comm.handle, lane, ticket, ctypes.byref(ok), ctypes.byref(fb), gt.ctypes.data))
+        return (bool(ok.value), int(fb.value), gt.tobytes()) if want_gt else (bool(ok.value), int(fb.value))
 
     def combine_partials_dev(self, d_partials, n_partials, want_gt=False):
         ok = ctypes.c_int(0)
@@ -327,6 +443,92 @@ class Engine:
         return v.value
 
 
+class KeyTable:
+    """Device-resident table of decoded public keys (b3_keytable_*): PublicKey::from_bytes -- decompression + key_validate,
+    M/src/keys.rs:140-147 -- paid once per validator; verification names keys by index.  Shared by every Engine of its device."""
+
+    def __init__(self, engine, capacity=0):
+        self.L = engine.L
+        self.engine = engine
+        h = ctypes.c_void_p()
+        engine._ck(self.L.b3_keytable_create(engine.handle, int(capacity), ctypes.byref(h)))
+        self.handle = h
+
+    def __len__(self):
+        return int(self.L.b3_keytable_size(self.handle))
+
+    def append(self, keys, compressed=True, validate=True):
+        """keys: bytes / uint8 array of 48-byte compressed (compressed=True) or 96-byte uncompressed records.
+        Returns (first_index, status[n])."""
+        rec = 48 if compressed else 96
+        _need(len(keys) % rec == 0, f"KeyTable.append: keys must be {rec}-byte records")
+        n = len(keys) // rec
+        p, keep = _buf(keys)
+        st = np.zeros(max(n, 1), dtype=np.int32)
+        first = ctypes.c_size_t(0)
+        self.engine._ck(self.L.b3_keytable_append(self.engine.handle, self.handle, p, n, 1 if compressed else 0, 1 if validate else 0,
+                                                  st.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.byref(first)))
+        return int(first.value), st[:n]
+
+    def get(self, idx):
+        kk = _u32(idx)
+        n = len(kk)
+        out = np.zeros(96 * max(n, 1), dtype=np.uint8)
+        st = np.zeros(max(n, 1), dtype=np.int32)
+        self.engine._ck(self.L.b3_keytable_get(self.engine.handle, self.handle, kk.ctypes.data, n, out.ctypes.data,
+                                               st.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        return out[:96 * n].reshape(n, 96), st[:n]
+
+    def close(self):
+        if self.handle:
+            self.L.b3_keytable_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def nccl_unique_id():
+    """128-byte NCCL unique id (call on one rank, ship to the others by any transport)."""
+    buf = np.zeros(128, dtype=np.uint8)
+    rc = _lib.lib().b3_nccl_unique_id(buf.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("milagro_bls_b200: NCCL not available (libnccl.so.2 could not be bound)")
+    return buf.tobytes()
+
+
+class Comm:
+    """b3_comm: one NCCL communicator serving `lanes` contexts of this process (see include/milagro_bls_b200.h)."""
+
+    def __init__(self, device, nranks, rank, unique_id, lanes=1):
+        self.L = _lib.lib()
+        h = ctypes.c_void_p()
+        idb = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy() if unique_id is not None else None
+        rc = self.L.b3_comm_create(int(device), int(nranks), int(rank), None if idb is None else idb.ctypes.data, int(lanes), ctypes.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"milagro_bls_b200: b3_comm_create failed (code {rc})")
+        self.handle = h
+        self.nranks, self.rank, self.lanes = nranks, rank, lanes
+
+    @property
+    def collectives(self):
+        return int(self.L.b3_comm_collective_count(self.handle))
+
+    def close(self):
+        if self.handle:
+            self.L.b3_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 _default = threading.local()
 
 
@@ -351,6 +553,7 @@ class PublicKey:
 
     def __init__(self, point):
         self.point = bytes(point)
+        _need(len(self.point) == 96, "PublicKey.point is the 96-byte uncompressed encoding")
 
     @staticmethod
     def from_bytes(data, engine=None):                       # keys.rs:140-147 (validates)
@@ -410,6 +613,7 @@ class AggregatePublicKey:
 
     def __init__(self, point=G1_INF):
         self.point = bytes(point)
+        _need(len(self.point) == 96, "AggregatePublicKey.point is the 96-byte uncompressed encoding")
 
     @staticmethod
     def aggregate(keys, engine=None):                        # aggregates.rs:29-39
@@ -453,6 +657,7 @@ class Signature:
 
     def __init__(self, point):
         self.point = bytes(point)
+        _need(len(self.point) == 192, "Signature.point is the 192-byte uncompressed encoding")
 
     @staticmethod
     def from_bytes(data, engine=None):                       # signature.rs:43-46 (no subgroup check)
@@ -489,6 +694,7 @@ class AggregateSignature:
 
     def __init__(self, point=G2_INF):                        # AggregateSignature::new, aggregates.rs:93-95
         self.point = bytes(point)
+        _need(len(self.point) == 192, "AggregateSignature.point is the 192-byte uncompressed encoding")
 
     @staticmethod
     def aggregate(signatures, engine=None):                  # aggregates.rs:100-106
@@ -548,18 +754,18 @@ class AggregateSignature:
         if n == 0:
             return True
         sigs = b"".join(s.point for s, _, _ in sets)
-        st, ok = e.g2_subgroup_check(sigs)
-        for i in range(n):
-            if st[i]:
-                _raise(int(st[i]))
-        bad = [i for i in range(n) if not ok[i]]
-        n_draw = bad[0] if bad else n
+        # phase one (b3_sig_precheck): parse + subgroup-check every signature ONCE; they stay in the context for phase two
+        try:
+            first_bad = e.sig_precheck(sigs)
+        except AmclError:
+            raise
+        n_draw = first_bad if first_bad >= 0 else n
         scalars = [draw_scalar(rng) for _ in range(n_draw)]
-        if bad:
+        if first_bad >= 0:
             return False
         msgs = [bytes(m) for _, _, m in sets]
-        accept, first_bad = e.verify_multiple(sigs, b"".join(k.point for _, k, _ in sets), None, b"".join(msgs), _offsets(msgs),
-                                              np.array(scalars, dtype=np.uint64))
+        accept = e.verify_multiple_checked(b"".join(k.point for _, k, _ in sets), None, b"".join(msgs), _offsets(msgs),
+                                           np.array(scalars, dtype=np.uint64))
         return accept
 
     def __eq__(self, o):

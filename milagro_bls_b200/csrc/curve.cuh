@@ -373,59 +373,86 @@ B3_FN_NOINLINE void g2_clear_cofactor(jac<F2>& r, const jac<F2>& p) {
 
 // ---- wire formats (ZCash uncompressed; A/bls381/core.rs:177-190, 344-364) -----------------------
 // G1: x || y (48-byte big-endian each); G2: x.im || x.re || y.im || y.re; infinity = 0x40 then zeros.
+// Records travel as 16-byte words (fp.cuh: wire_load / wire_store -- LDG.128 / STG.128 on aligned arrays).
 B3_FN_NOINLINE void g1_aff_to_wire(uint8_t* out, const g1_aff& a) {
-    if (a.inf) { for (int i = 0; i < 96; i++) out[i] = 0; out[0] = 0x40; return; }
-    fp t;
-    fp_from_mont(t, a.x); fp_raw_to_be(out, t);
-    fp_from_mont(t, a.y); fp_raw_to_be(out + 48, t);
+    b3_q16 q[6];
+    if (a.inf) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) { q[i].x = 0; q[i].y = 0; q[i].z = 0; q[i].w = 0; }
+        q[0].x = 0x40;
+    } else {
+        fp t;
+        fp_from_mont(t, a.x); fp_raw_to_q(q, t);
+        fp_from_mont(t, a.y); fp_raw_to_q(q + 3, t);
+    }
+    wire_store<6>(out, q);
 }
 B3_FN_NOINLINE void g2_aff_to_wire(uint8_t* out, const g2_aff& a) {
-    if (a.inf) { for (int i = 0; i < 192; i++) out[i] = 0; out[0] = 0x40; return; }
-    fp t;
-    fp_from_mont(t, a.x.c1); fp_raw_to_be(out, t);
-    fp_from_mont(t, a.x.c0); fp_raw_to_be(out + 48, t);
-    fp_from_mont(t, a.y.c1); fp_raw_to_be(out + 96, t);
-    fp_from_mont(t, a.y.c0); fp_raw_to_be(out + 144, t);
+    b3_q16 q[12];
+    if (a.inf) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) { q[i].x = 0; q[i].y = 0; q[i].z = 0; q[i].w = 0; }
+        q[0].x = 0x40;
+    } else {
+        fp t;
+        fp_from_mont(t, a.x.c1); fp_raw_to_q(q, t);
+        fp_from_mont(t, a.x.c0); fp_raw_to_q(q + 3, t);
+        fp_from_mont(t, a.y.c1); fp_raw_to_q(q + 6, t);
+        fp_from_mont(t, a.y.c0); fp_raw_to_q(q + 9, t);
+    }
+    wire_store<12>(out, q);
 }
 // status codes shared with the C ABI (mirror A/errors.rs:1-11)
 #define B3_OK 0
 #define B3_ERR_INVALID_POINT (-5)
 #define B3_ERR_INVALID_YFLAG (-8)
-// Parse without the on-curve check (caller decides); returns B3_OK or an error code.
-B3_FN_NOINLINE int g1_aff_from_wire(g1_aff& r, const uint8_t* in) {
-    if (in[0] & 0x80) return B3_ERR_INVALID_POINT;          // compressed flag on a 96-byte buffer
-    if (in[0] & 0x40) {
-        uint32_t acc = in[0] & 0x3f;
-        for (int i = 1; i < 96; i++) acc |= in[i];
+// Parse a record held as 16-byte words, without the on-curve check (caller decides); returns B3_OK or an error code.
+// Byte 0 of the record (the flag byte) is the low byte of q[0].x.
+B3_FN_NOINLINE int g1_aff_from_q(g1_aff& r, const b3_q16* q) {
+    const uint32_t b0 = q[0].x & 0xffu;
+    if (b0 & 0x80) return B3_ERR_INVALID_POINT;             // compressed flag on a 96-byte buffer
+    if (b0 & 0x40) {
+        const uint32_t acc = (q[0].x & 0xffffff3fu) | q[0].y | q[0].z | q[0].w | b3_q16_or(q + 1, 5);
         if (acc) return B3_ERR_INVALID_POINT;
         r.x = FP_NIL; r.y = FP_NIL; r.inf = 1;
         return B3_OK;
     }
-    if (in[0] & 0x20) return B3_ERR_INVALID_YFLAG;
+    if (b0 & 0x20) return B3_ERR_INVALID_YFLAG;
     fp x, y;
-    fp_raw_from_be(x, in);
-    fp_raw_from_be(y, in + 48);
+    fp_raw_from_q(x, q);
+    fp_raw_from_q(y, q + 3);
     if (!fp_raw_lt_p(x) || !fp_raw_lt_p(y)) return B3_ERR_INVALID_POINT;
     fp_to_mont(r.x, x); fp_to_mont(r.y, y); r.inf = 0;
     return B3_OK;
 }
-B3_FN_NOINLINE int g2_aff_from_wire(g2_aff& r, const uint8_t* in) {
-    if (in[0] & 0x80) return B3_ERR_INVALID_POINT;
-    if (in[0] & 0x40) {
-        uint32_t acc = in[0] & 0x3f;
-        for (int i = 1; i < 192; i++) acc |= in[i];
+B3_FN_NOINLINE int g1_aff_from_wire(g1_aff& r, const uint8_t* in) {
+    b3_q16 q[6];
+    wire_load<6>(q, in);
+    return g1_aff_from_q(r, q);
+}
+B3_FN_NOINLINE int g2_aff_from_q(g2_aff& r, const b3_q16* q) {
+    const uint32_t b0 = q[0].x & 0xffu;
+    if (b0 & 0x80) return B3_ERR_INVALID_POINT;
+    if (b0 & 0x40) {
+        const uint32_t acc = (q[0].x & 0xffffff3fu) | q[0].y | q[0].z | q[0].w | b3_q16_or(q + 1, 11);
         if (acc) return B3_ERR_INVALID_POINT;
         fp2_zero(r.x); fp2_zero(r.y); r.inf = 1;
         return B3_OK;
     }
-    if (in[0] & 0x20) return B3_ERR_INVALID_YFLAG;
+    if (b0 & 0x20) return B3_ERR_INVALID_YFLAG;
     fp v[4];
+#pragma unroll
     for (int k = 0; k < 4; k++) {
-        fp_raw_from_be(v[k], in + 48 * k);
+        fp_raw_from_q(v[k], q + 3 * k);
         if (!fp_raw_lt_p(v[k])) return B3_ERR_INVALID_POINT;
     }
     fp_to_mont(r.x.c1, v[0]); fp_to_mont(r.x.c0, v[1]);
     fp_to_mont(r.y.c1, v[2]); fp_to_mont(r.y.c0, v[3]);
     r.inf = 0;
     return B3_OK;
+}
+B3_FN_NOINLINE int g2_aff_from_wire(g2_aff& r, const uint8_t* in) {
+    b3_q16 q[12];
+    wire_load<12>(q, in);
+    return g2_aff_from_q(r, q);
 }

@@ -554,18 +554,76 @@ B3_FN_NOINLINE bool fp_sqrt_ratio_parts(fp& t, fp& tinv, const fp& d) {
 // canonical integer comparison helpers (inputs canonical, NOT Montgomery)
 B3_FN bool fp_raw_lt_p(const fp& a) { return fp_raw_gt(FP_P, a); }
 
-// 48 big-endian bytes <-> raw limbs
-B3_FN void fp_raw_from_be(fp& r, const uint8_t* b) {
+// ------------------------------------------------------------------------------------------------
+// Wire loads / stores, 16 bytes at a time.  Every record of the wire formats is a multiple of 16 bytes (48 / 96 / 192),
+// so a 16-byte-aligned array is read with LDG.128 and byte-swapped in registers (PRMT).
+// ------------------------------------------------------------------------------------------------
+#if defined(B3_HOSTSIM)
+struct b3_q16 { uint32_t x, y, z, w; };
+static inline uint32_t b3_bswap(uint32_t v) { return __builtin_bswap32(v); }
+#else
+typedef uint4 b3_q16;
+__device__ __forceinline__ uint32_t b3_bswap(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+#endif
+B3_FN bool b3_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+B3_FN void b3_q16_from_bytes(b3_q16& q, const uint8_t* b) {
+    q.x = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+    q.y = (uint32_t)b[4] | ((uint32_t)b[5] << 8) | ((uint32_t)b[6] << 16) | ((uint32_t)b[7] << 24);
+    q.z = (uint32_t)b[8] | ((uint32_t)b[9] << 8) | ((uint32_t)b[10] << 16) | ((uint32_t)b[11] << 24);
+    q.w = (uint32_t)b[12] | ((uint32_t)b[13] << 8) | ((uint32_t)b[14] << 16) | ((uint32_t)b[15] << 24);
+}
+B3_FN void b3_q16_to_bytes(uint8_t* b, const b3_q16& q) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-    for (int i = 0; i < 12; i++) {
-        const uint8_t* q = b + 44 - 4 * i;
-        r.l[i] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3];
-    }
+    for (int i = 0; i < 4; i++) { b[4 * i] = (uint8_t)w[i]; b[4 * i + 1] = (uint8_t)(w[i] >> 8); b[4 * i + 2] = (uint8_t)(w[i] >> 16); b[4 * i + 3] = (uint8_t)(w[i] >> 24); }
+}
+// N16 16-byte words of a wire record.  Device arrays are 16-byte aligned by contract: the host-pointer entries stage into the
+// context's own buffers, the *_dev entries reject unaligned pointers (capi.cu: dev_aligned), so the device path is LDG.128 /
+// STG.128 only.  The host build (tests/hostsim) takes any pointer.
+template <int N16>
+B3_FN void wire_load(b3_q16* q, const uint8_t* in) {
+#if defined(B3_HOSTSIM)
+    for (int i = 0; i < N16; i++) b3_q16_from_bytes(q[i], in + 16 * i);
+#else
+#pragma unroll
+    for (int i = 0; i < N16; i++) q[i] = __ldg(reinterpret_cast<const uint4*>(in) + i);
+#endif
+}
+template <int N16>
+B3_FN void wire_store(uint8_t* out, const b3_q16* q) {
+#if defined(B3_HOSTSIM)
+    for (int i = 0; i < N16; i++) b3_q16_to_bytes(out + 16 * i, q[i]);
+#else
+#pragma unroll
+    for (int i = 0; i < N16; i++) reinterpret_cast<uint4*>(out)[i] = q[i];
+#endif
+}
+// 48 big-endian bytes held as three 16-byte words <-> raw limbs (limb i = byte-swapped word 11 - i)
+B3_FN void fp_raw_from_q(fp& r, const b3_q16* q) {
+    r.l[0] = b3_bswap(q[2].w); r.l[1] = b3_bswap(q[2].z); r.l[2] = b3_bswap(q[2].y); r.l[3] = b3_bswap(q[2].x);
+    r.l[4] = b3_bswap(q[1].w); r.l[5] = b3_bswap(q[1].z); r.l[6] = b3_bswap(q[1].y); r.l[7] = b3_bswap(q[1].x);
+    r.l[8] = b3_bswap(q[0].w); r.l[9] = b3_bswap(q[0].z); r.l[10] = b3_bswap(q[0].y); r.l[11] = b3_bswap(q[0].x);
+}
+B3_FN void fp_raw_to_q(b3_q16* q, const fp& a) {
+    q[2].w = b3_bswap(a.l[0]); q[2].z = b3_bswap(a.l[1]); q[2].y = b3_bswap(a.l[2]); q[2].x = b3_bswap(a.l[3]);
+    q[1].w = b3_bswap(a.l[4]); q[1].z = b3_bswap(a.l[5]); q[1].y = b3_bswap(a.l[6]); q[1].x = b3_bswap(a.l[7]);
+    q[0].w = b3_bswap(a.l[8]); q[0].z = b3_bswap(a.l[9]); q[0].y = b3_bswap(a.l[10]); q[0].x = b3_bswap(a.l[11]);
+}
+// OR of the words of n 16-byte words (all-zero test of a record)
+B3_FN uint32_t b3_q16_or(const b3_q16* q, int n) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < n; i++) acc |= q[i].x | q[i].y | q[i].z | q[i].w;
+    return acc;
+}
+// 48 big-endian bytes <-> raw limbs through a byte pointer (any alignment)
+B3_FN void fp_raw_from_be(fp& r, const uint8_t* b) {
+    b3_q16 q[3];
+    wire_load<3>(q, b);
+    fp_raw_from_q(r, q);
 }
 B3_FN void fp_raw_to_be(uint8_t* b, const fp& a) {
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-        uint8_t* q = b + 44 - 4 * i;
-        q[0] = (uint8_t)(a.l[i] >> 24); q[1] = (uint8_t)(a.l[i] >> 16); q[2] = (uint8_t)(a.l[i] >> 8); q[3] = (uint8_t)a.l[i];
-    }
+    b3_q16 q[3];
+    fp_raw_to_q(q, a);
+    wire_store<3>(b, q);
 }

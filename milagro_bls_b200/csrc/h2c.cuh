@@ -70,7 +70,24 @@ B3_FN void sha256_put(sha256_ctx& c, uint8_t byte) {
         c.fill = 0;
     }
 }
-B3_FN void sha256_update(sha256_ctx& c, const uint8_t* p, uint32_t n) { for (uint32_t i = 0; i < n; i++) sha256_put(c, p[i]); }
+// four bytes at once (the block buffer holds big-endian words): only at a word boundary of the block
+B3_FN void sha256_put_word(sha256_ctx& c, uint32_t be_word) {
+    c.w[c.fill >> 2] = be_word;
+    c.fill += 4; c.total += 4;
+    if (c.fill == 64) {
+        sha256_compress(c.h, c.w);
+        for (int i = 0; i < 16; i++) c.w[i] = 0;
+        c.fill = 0;
+    }
+}
+B3_FN void sha256_update(sha256_ctx& c, const uint8_t* p, uint32_t n) {
+    uint32_t i = 0;
+#if !defined(B3_HOSTSIM)
+    if ((reinterpret_cast<uintptr_t>(p) & 3u) == 0 && (c.fill & 3u) == 0)        // aligned input: 32-bit loads
+        for (; i + 4 <= n; i += 4) sha256_put_word(c, b3_bswap(__ldg(reinterpret_cast<const uint32_t*>(p + i))));
+#endif
+    for (; i < n; i++) sha256_put(c, p[i]);
+}
 B3_FN void sha256_final(sha256_ctx& c, uint32_t* out8) {
     uint64_t bits = c.total * 8;
     sha256_put(c, 0x80);

@@ -65,26 +65,25 @@ __global__ void __launch_bounds__(B3_TPB) k_g1_key_validate(const g1_jac* pts, c
 }
 
 // ------------------------------------------------------------------------------------------------ (de)compression
-__global__ void __launch_bounds__(B3_TPB) k_g1_decompress(const uint8_t* __restrict__ in, size_t n, int validate, uint8_t* out, int32_t* status) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint8_t* b = in + 48 * i;
-    uint8_t* o = out + 96 * i;
+// Records are read and written as 16-byte words (wire_load / wire_store: LDG.128 / STG.128 on aligned arrays).
+template <int N16>
+__device__ __forceinline__ void q16_zero(b3_q16* q) {
+#pragma unroll
+    for (int i = 0; i < N16; i++) { q[i].x = 0; q[i].y = 0; q[i].z = 0; q[i].w = 0; }
+}
+// ZCash-compressed G1 record (three 16-byte words) -> affine point, optional key_validate (M/src/keys.rs:140-147,181-186)
+__device__ __noinline__ int g1_decompress_q(g1_aff& a, const b3_q16* qin, int validate) {
     int e = B3_OK;
-    g1_aff a;
     a.x = FP_NIL; a.y = FP_NIL; a.inf = 1;
-    uint8_t b0 = b[0];
+    b3_q16 q[3] = {qin[0], qin[1], qin[2]};
+    const uint32_t b0 = q[0].x & 0xffu;
     if (!(b0 & 0x80)) e = B3_ERR_INVALID_G1_SIZE_D;          // 48 bytes without the C flag: routed to the 96-byte parser
     else if (b0 & 0x40) {
-        uint32_t acc = b0 & 0x3f;
-        for (int k = 1; k < 48; k++) acc |= b[k];
-        if (acc) e = B3_ERR_INVALID_POINT;
+        if ((q[0].x & 0xffffff3fu) | q[0].y | q[0].z | q[0].w | b3_q16_or(q + 1, 2)) e = B3_ERR_INVALID_POINT;
     } else {
-        uint8_t tmp[48];
-        for (int k = 0; k < 48; k++) tmp[k] = b[k];
-        tmp[0] &= 0x1f;
+        q[0].x &= 0xffffff1fu;
         fp x;
-        fp_raw_from_be(x, tmp);
+        fp_raw_from_q(x, q);
         if (!fp_raw_lt_p(x)) e = B3_ERR_INVALID_POINT;
         else {
             fp xm, rhs, t, y, yinv;
@@ -114,32 +113,104 @@ __global__ void __launch_bounds__(B3_TPB) k_g1_decompress(const uint8_t* __restr
         pt_from_aff(j, a);
         if (a.inf || !g1_in_subgroup(j)) e = B3_ERR_INVALID_POINT;
     }
-    if (e) { for (int k = 0; k < 96; k++) o[k] = 0; }
+    return e;
+}
+__global__ void __launch_bounds__(B3_TPB) k_g1_decompress(const uint8_t* __restrict__ in, size_t n, int validate, uint8_t* out, int32_t* status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t* o = out + 96 * i;
+    g1_aff a;
+    b3_q16 q[3];
+    wire_load<3>(q, in + 48 * i);
+    const int e = g1_decompress_q(a, q, validate);
+    if (e) { b3_q16 z[6]; q16_zero<6>(z); wire_store<6>(o, z); }
     else g1_aff_to_wire(o, a);
+    status[i] = e;
+}
+
+// ---- device-resident public-key table (the reference pays PublicKey::from_bytes -- decompression + key_validate,
+// M/src/keys.rs:140-147 -- once per validator and then aggregates the decoded points, M/src/aggregates.rs:29-39) ----------------
+// Entry = (x, y) in Montgomery form, 96 bytes, read with six LDG.128 and used as is: no byte swap, no conversion, no checks per
+// use.  (0, 0) encodes infinity (it is not on the curve); x.l[11] = 0xffffffff (> p) marks an entry whose input was rejected.
+struct key_entry {
+    fp x, y;
+};
+#define B3_KEY_INVALID 0xffffffffu
+__global__ void __launch_bounds__(B3_TPB) k_keytable_build(const uint8_t* __restrict__ in, size_t n, int compressed, int validate, key_entry* out,
+                                                           int32_t* status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g1_aff a;
+    int e;
+    if (compressed) {
+        b3_q16 q[3];
+        wire_load<3>(q, in + 48 * i);
+        e = g1_decompress_q(a, q, validate);
+    } else {
+        e = g1_aff_from_wire(a, in + 96 * i);
+        if (e == B3_OK && !pt_on_curve_aff(a)) e = B3_ERR_INVALID_POINT;
+        if (e == B3_OK && validate) {
+            g1_jac j;
+            pt_from_aff(j, a);
+            if (a.inf || !g1_in_subgroup(j)) e = B3_ERR_INVALID_POINT;
+        }
+    }
+    key_entry k;
+    if (e) { k.x = FP_NIL; k.y = FP_NIL; k.x.l[11] = B3_KEY_INVALID; }
+    else if (a.inf) { k.x = FP_NIL; k.y = FP_NIL; }
+    else { k.x = a.x; k.y = a.y; }
+    out[i] = k;
+    status[i] = e;
+}
+__device__ __forceinline__ void key_entry_load(key_entry& k, const key_entry* p) {
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&k);
+#pragma unroll
+    for (int j = 0; j < 6; j++) d[j] = __ldg(s + j);
+}
+// table entry -> affine point; returns B3_ERR_INVALID_POINT for a rejected entry
+__device__ __forceinline__ int key_entry_point(g1_aff& a, const key_entry& k) {
+    if (k.x.l[11] == B3_KEY_INVALID) return B3_ERR_INVALID_POINT;
+    a.x = k.x; a.y = k.y;
+    a.inf = (fp_is_zero(k.x) && fp_is_zero(k.y)) ? 1u : 0u;
+    return B3_OK;
+}
+__global__ void __launch_bounds__(B3_TPB) k_keytable_get(const key_entry* __restrict__ table, size_t n_table, const uint32_t* __restrict__ idx, size_t n,
+                                                         uint8_t* out96, int32_t* status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = idx[i];
+    g1_aff a;
+    a.x = FP_NIL; a.y = FP_NIL; a.inf = 1;
+    int e = B3_ERR_INVALID_POINT;
+    if (k < n_table) {
+        key_entry ent;
+        key_entry_load(ent, table + k);
+        e = key_entry_point(a, ent);
+    }
+    if (e) { b3_q16 z[6]; q16_zero<6>(z); wire_store<6>(out96 + 96 * i, z); }
+    else g1_aff_to_wire(out96 + 96 * i, a);
     status[i] = e;
 }
 
 __global__ void __launch_bounds__(B3_TPB) k_g2_decompress(const uint8_t* __restrict__ in, size_t n, uint8_t* out, int32_t* status) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint8_t* b = in + 96 * i;
     uint8_t* o = out + 192 * i;
     int e = B3_OK;
     g2_aff a;
     fp2_zero(a.x); fp2_zero(a.y); a.inf = 1;
-    uint8_t b0 = b[0];
+    b3_q16 q[6];
+    wire_load<6>(q, in + 96 * i);
+    const uint32_t b0 = q[0].x & 0xffu;
     if (!(b0 & 0x80)) e = B3_ERR_INVALID_G2_SIZE_D;
     else if (b0 & 0x40) {
-        uint32_t acc = b0 & 0x3f;
-        for (int k = 1; k < 96; k++) acc |= b[k];
-        if (acc) e = B3_ERR_INVALID_POINT;
+        if ((q[0].x & 0xffffff3fu) | q[0].y | q[0].z | q[0].w | b3_q16_or(q + 1, 5)) e = B3_ERR_INVALID_POINT;
     } else {
-        uint8_t tmp[48];
-        for (int k = 0; k < 48; k++) tmp[k] = b[k];
-        tmp[0] &= 0x1f;
+        q[0].x &= 0xffffff1fu;
         fp xim, xre;
-        fp_raw_from_be(xim, tmp);
-        fp_raw_from_be(xre, b + 48);
+        fp_raw_from_q(xim, q);
+        fp_raw_from_q(xre, q + 3);
         if (!fp_raw_lt_p(xim) || !fp_raw_lt_p(xre)) e = B3_ERR_INVALID_POINT;
         else {
             fp2 x, rhs, t, y;
@@ -172,7 +243,7 @@ __global__ void __launch_bounds__(B3_TPB) k_g2_decompress(const uint8_t* __restr
             }
         }
     }
-    if (e) { for (int k = 0; k < 192; k++) o[k] = 0; }
+    if (e) { b3_q16 z[12]; q16_zero<12>(z); wire_store<12>(o, z); }
     else g2_aff_to_wire(o, a);
     status[i] = e;
 }
@@ -181,39 +252,47 @@ __global__ void __launch_bounds__(B3_TPB) k_g1_compress(const uint8_t* __restric
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g1_aff a;
-    uint8_t* o = out + 48 * i;
     int e = g1_aff_from_wire(a, in + 96 * i);
-    for (int k = 0; k < 48; k++) o[k] = 0;
     status[i] = e;
-    if (e) return;
-    if (a.inf) { o[0] = 0xc0; return; }
-    fp xc, yc, ny, nyc;
-    fp_from_mont(xc, a.x);
-    fp_from_mont(yc, a.y);
-    fp_neg(ny, a.y);
-    fp_from_mont(nyc, ny);
-    fp_raw_to_be(o, xc);
-    o[0] |= 0x80 | (fp_raw_gt(yc, nyc) ? 0x20 : 0);
+    b3_q16 q[3];
+    q16_zero<3>(q);
+    if (e == B3_OK) {
+        if (a.inf) q[0].x = 0xc0;
+        else {
+            fp xc, yc, ny, nyc;
+            fp_from_mont(xc, a.x);
+            fp_from_mont(yc, a.y);
+            fp_neg(ny, a.y);
+            fp_from_mont(nyc, ny);
+            fp_raw_to_q(q, xc);
+            q[0].x |= 0x80u | (fp_raw_gt(yc, nyc) ? 0x20u : 0u);
+        }
+    }
+    wire_store<3>(out + 48 * i, q);
 }
 __global__ void __launch_bounds__(B3_TPB) k_g2_compress(const uint8_t* __restrict__ in, size_t n, uint8_t* out, int32_t* status) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g2_aff a;
-    uint8_t* o = out + 96 * i;
     int e = g2_aff_from_wire(a, in + 192 * i);
-    for (int k = 0; k < 96; k++) o[k] = 0;
     status[i] = e;
-    if (e) return;
-    if (a.inf) { o[0] = 0xc0; return; }
-    fp t, yi, yr, nyi, nyr;
-    fp2 ny;
-    fp2_neg(ny, a.y);
-    fp_from_mont(t, a.x.c1); fp_raw_to_be(o, t);
-    fp_from_mont(t, a.x.c0); fp_raw_to_be(o + 48, t);
-    fp_from_mont(yi, a.y.c1); fp_from_mont(yr, a.y.c0);
-    fp_from_mont(nyi, ny.c1); fp_from_mont(nyr, ny.c0);
-    bool greater = fp_raw_gt(yi, nyi) || (fp_eq(yi, nyi) && fp_raw_gt(yr, nyr));
-    o[0] |= 0x80 | (greater ? 0x20 : 0);
+    b3_q16 q[6];
+    q16_zero<6>(q);
+    if (e == B3_OK) {
+        if (a.inf) q[0].x = 0xc0;
+        else {
+            fp t, yi, yr, nyi, nyr;
+            fp2 ny;
+            fp2_neg(ny, a.y);
+            fp_from_mont(t, a.x.c1); fp_raw_to_q(q, t);
+            fp_from_mont(t, a.x.c0); fp_raw_to_q(q + 3, t);
+            fp_from_mont(yi, a.y.c1); fp_from_mont(yr, a.y.c0);
+            fp_from_mont(nyi, ny.c1); fp_from_mont(nyr, ny.c0);
+            bool greater = fp_raw_gt(yi, nyi) || (fp_eq(yi, nyi) && fp_raw_gt(yr, nyr));
+            q[0].x |= 0x80u | (greater ? 0x20u : 0u);
+        }
+    }
+    wire_store<6>(out + 96 * i, q);
 }
 
 // ------------------------------------------------------------------------------------------------ aggregation
@@ -227,22 +306,110 @@ __device__ __forceinline__ void shfl_down_struct(P& dst, const P& src, int delta
     for (int k = 0; k < (int)(sizeof(P) / 4); k++) d[k] = __shfl_down_sync(0xffffffffu, s[k], delta, width);
 }
 
+// The keys are the bulk of the input bytes (C4: 100 MB of 103 MB), so they are STAGED: the G lanes of a group fetch the group's
+// next run of G consecutive 96-byte records as 16-byte words, lane l taking words l, l + G, ... (LDG.128, each warp request
+// covering 8 x G*16 contiguous bytes), one step AHEAD of the additions (the loads of step t + 1 are in flight while the
+// mixed additions of step t execute); the words pass through shared memory to reach the lane that owns the record.
+// check_curve: reject keys that are not on the curve (the reference's types cannot hold such a point: every constructor
+// of PublicKey checks, M/src/keys.rs:140-175; pt_add_aff never uses the curve constant, so an unchecked key would
+// silently run the arithmetic on another curve).
 template <int G>
 __global__ void __launch_bounds__(B3_TPB) k_g1_aggregate(const uint8_t* __restrict__ pks, const uint32_t* __restrict__ off, size_t n_sets,
-                                                         g1_jac* out, int32_t* status) {
+                                                         g1_jac* out, int32_t* status, int check_curve) {
+    __shared__ b3_q16 stage[B3_TPB * 6];                    // one 96-byte record per thread
     size_t gid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    int lane = threadIdx.x % G;
+    const int lane = threadIdx.x % G;
+    bool active = gid < n_sets;
+    uint32_t b = 0, e = 0;
+    if (active) { b = off[gid]; e = off[gid + 1]; }
+    b3_q16* const run = stage + (size_t)(threadIdx.x - lane) * 6;
+    const uint4* const base16 = reinterpret_cast<const uint4*>(pks);
+    g1_jac acc;
+    pt_set_inf(acc);
+    int err = 0;
+    b3_q16 nxt[6];
+    uint32_t i0 = b;
+    // fetch the run [i0, i0 + G) of this group (clipped to the set): this lane takes words lane, lane + G, ..
+#define B3_AGG_FETCH()                                                                                          \
+    do {                                                                                                        \
+        const uint32_t recs = i0 < e ? (e - i0 < (uint32_t)G ? e - i0 : (uint32_t)G) : 0u;                      \
+        _Pragma("unroll") for (int j = 0; j < 6; j++) {                                                         \
+            const uint32_t w = (uint32_t)lane + (uint32_t)G * j;                                                \
+            if (w < recs * 6) nxt[j] = __ldg(base16 + (size_t)i0 * 6 + w);                                      \
+        }                                                                                                       \
+    } while (0)
+    B3_AGG_FETCH();
+    while (__any_sync(0xffffffffu, i0 < e)) {              // warp-uniform trip count (ragged sets): the staging syncs the warp
+        b3_q16 q[6];
+#pragma unroll
+        for (int j = 0; j < 6; j++) run[lane + G * j] = nxt[j];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 6; j++) q[j] = run[lane * 6 + j];
+        __syncwarp();
+        const bool mine = i0 < e && i0 + lane < e;
+        if (i0 < e) i0 += G;
+        B3_AGG_FETCH();
+        if (mine) {
+            g1_aff a;
+            int s = g1_aff_from_q(a, q);
+            if (s == B3_OK && check_curve && !pt_on_curve_aff(a)) s = B3_ERR_INVALID_POINT;
+            if (s) err = s;
+            else pt_add_aff(acc, acc, a);
+        }
+    }
+#undef B3_AGG_FETCH
+#pragma unroll 1
+    for (int d = G / 2; d >= 1; d >>= 1) {
+        g1_jac o;
+        shfl_down_struct(o, acc, d, G);
+        int oe = __shfl_down_sync(0xffffffffu, err, d, G);
+        if (lane < d) {
+            pt_add(acc, acc, o);
+            if (oe) err = oe;
+        }
+    }
+    if (active && lane == 0) {
+        if (b == e) err = B3_ERR_AGGREGATE_EMPTY_POINTS_D;
+        out[gid] = acc;
+        status[gid] = err;
+    }
+}
+// The same aggregation over a device-resident key table: set s owns the table entries idx[off[s] .. off[s+1]).  A gather of
+// 96-byte entries (three full 32-byte sectors each), the next entry in flight while the current one is added.
+template <int G>
+__global__ void __launch_bounds__(B3_TPB) k_g1_aggregate_idx(const key_entry* __restrict__ table, size_t n_table, const uint32_t* __restrict__ idx,
+                                                             const uint32_t* __restrict__ off, size_t n_sets, g1_jac* out, int32_t* status) {
+    size_t gid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x % G;
     bool active = gid < n_sets;
     uint32_t b = 0, e = 0;
     if (active) { b = off[gid]; e = off[gid + 1]; }
     g1_jac acc;
     pt_set_inf(acc);
     int err = 0;
-    for (uint32_t i = b + lane; i < e; i += G) {
+    uint32_t i = b + lane;
+    bool have = i < e, ok = false;
+    key_entry cur, nxt;
+    if (have) {
+        const uint32_t k = idx[i];
+        ok = k < n_table;
+        if (ok) key_entry_load(cur, table + k);
+    }
+    while (have) {
+        const uint32_t inext = i + G;
+        const bool hn = inext < e;
+        bool okn = false;
+        if (hn) {
+            const uint32_t k = idx[inext];
+            okn = k < n_table;
+            if (okn) key_entry_load(nxt, table + k);
+        }
         g1_aff a;
-        int s = g1_aff_from_wire(a, pks + 96 * (size_t)i);
+        int s = ok ? key_entry_point(a, cur) : B3_ERR_INVALID_POINT;
         if (s) err = s;
         else pt_add_aff(acc, acc, a);
+        cur = nxt; ok = okn; have = hn; i = inext;
     }
 #pragma unroll 1
     for (int d = G / 2; d >= 1; d >>= 1) {
@@ -260,10 +427,10 @@ __global__ void __launch_bounds__(B3_TPB) k_g1_aggregate(const uint8_t* __restri
         status[gid] = err;
     }
 }
-// G2 aggregation (AggregateSignature::aggregate): same shape over Fp2
+// G2 aggregation (AggregateSignature::aggregate): same shape over Fp2 (records read as 12 x LDG.128 per lane)
 template <int G>
 __global__ void __launch_bounds__(B3_TPB) k_g2_aggregate(const uint8_t* __restrict__ sigs, const uint32_t* __restrict__ off, size_t n_sets,
-                                                         g2_jac* out, int32_t* status) {
+                                                         g2_jac* out, int32_t* status, int check_curve) {
     size_t gid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
     int lane = threadIdx.x % G;
     bool active = gid < n_sets;
@@ -275,6 +442,7 @@ __global__ void __launch_bounds__(B3_TPB) k_g2_aggregate(const uint8_t* __restri
     for (uint32_t i = b + lane; i < e; i += G) {
         g2_aff a;
         int s = g2_aff_from_wire(a, sigs + 192 * (size_t)i);
+        if (s == B3_OK && check_curve && !pt_on_curve_aff(a)) s = B3_ERR_INVALID_POINT;
         if (s) err = s;
         else pt_add_aff(acc, acc, a);
     }
@@ -307,10 +475,10 @@ __global__ void __launch_bounds__(B3_TPB) k_g2_mul_u64(const g2_aff* in, const u
 }
 // 256-bit scalars (32-byte big-endian) -- input synthesis only
 __device__ __forceinline__ void load_scalar256(uint32_t* k, const uint8_t* b) {
-    for (int w = 0; w < 8; w++) {
-        const uint8_t* q = b + 28 - 4 * w;
-        k[w] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3];
-    }
+    b3_q16 q[2];
+    wire_load<2>(q, b);
+    k[0] = b3_bswap(q[1].w); k[1] = b3_bswap(q[1].z); k[2] = b3_bswap(q[1].y); k[3] = b3_bswap(q[1].x);
+    k[4] = b3_bswap(q[0].w); k[5] = b3_bswap(q[0].z); k[6] = b3_bswap(q[0].y); k[7] = b3_bswap(q[0].x);
 }
 __global__ void __launch_bounds__(B3_TPB) k_g1_mul_gen_u256(const uint8_t* __restrict__ scalars, size_t n, uint8_t* out96) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -465,21 +633,90 @@ __global__ void __launch_bounds__(B3_TPB) k_g2_add_pairs(const g2_jac* in, size_
 }
 
 // ------------------------------------------------------------------------------------------------ normalisation
-__global__ void __launch_bounds__(B3_TPB) k_g1_to_affine(const g1_jac* in, size_t n, g1_aff* out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    g1_jac p = in[i];
-    g1_aff a;
-    pt_to_aff(a, p);
-    out[i] = a;
+// Jacobian -> affine with MONTGOMERY'S TRICK: a thread normalises `per` consecutive points with ONE field
+// inversion -- prefix products of the Z's, one binary-Euclid inversion (fp_inv: data-dependent control flow, the expensive
+// and divergent part), then two multiplications per point to peel the individual inverses off.  The reference inverts once
+// per point with a Fermat exponentiation (A/ecp.rs:362-379, A/ecp2.rs:203-218); the affine values are the same.
+// G2: 1 / z = conj(z) / N(z), so the batch runs over the NORMS in Fp.
+#define B3_NORM_MAX 16
+__host__ __device__ __forceinline__ unsigned norm_per(size_t n) {          // points per thread: keep >= ~16 k threads
+    size_t k = n / 16384;
+    return k < 1 ? 1u : k > B3_NORM_MAX ? (unsigned)B3_NORM_MAX : (unsigned)k;
 }
-__global__ void __launch_bounds__(B3_TPB) k_g2_to_affine(const g2_jac* in, size_t n, g2_aff* out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    g2_jac p = in[i];
-    g2_aff a;
-    pt_to_aff(a, p);
-    out[i] = a;
+__global__ void __launch_bounds__(B3_TPB) k_g1_to_affine(const g1_jac* in, size_t n, g1_aff* out, unsigned per) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t first = t * per;
+    if (first >= n) return;
+    const unsigned cnt = (unsigned)(n - first < per ? n - first : per);
+    fp pre[B3_NORM_MAX];
+    fp acc = FP_ONE;
+    for (unsigned j = 0; j < cnt; j++) {
+        fp z = in[first + j].z;
+        if (fp_is_zero(z)) z = FP_ONE;
+        pre[j] = acc;
+        fp_mul(acc, acc, z);
+    }
+    fp inv;
+    fp_inv(inv, acc);
+    for (unsigned j = cnt; j-- > 0;) {
+        const g1_jac p = in[first + j];
+        g1_aff a;
+        if (fp_is_zero(p.z)) { a.x = FP_NIL; a.y = FP_NIL; a.inf = 1; }
+        else {
+            fp zi, zi2;
+            fp_mul(zi, inv, pre[j]);
+            fp_mul(inv, inv, p.z);
+            fp_sqr(zi2, zi);
+            fp_mul(a.x, p.x, zi2);
+            fp_mul(zi2, zi2, zi);
+            fp_mul(a.y, p.y, zi2);
+            a.inf = 0;
+        }
+        out[first + j] = a;
+    }
+}
+__global__ void __launch_bounds__(B3_TPB) k_g2_to_affine(const g2_jac* in, size_t n, g2_aff* out, unsigned per) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t first = t * per;
+    if (first >= n) return;
+    const unsigned cnt = (unsigned)(n - first < per ? n - first : per);
+    fp pre[B3_NORM_MAX];
+    fp acc = FP_ONE;
+    for (unsigned j = 0; j < cnt; j++) {
+        const fp2 z = in[first + j].z;
+        fp nz, t1;
+        fp_sqr(nz, z.c0);
+        fp_sqr(t1, z.c1);
+        fp_add(nz, nz, t1);                               // N(z) = 0 <=> z = 0 (-1 is not a square in Fp)
+        if (fp_is_zero(nz)) nz = FP_ONE;
+        pre[j] = acc;
+        fp_mul(acc, acc, nz);
+    }
+    fp inv;
+    fp_inv(inv, acc);
+    for (unsigned j = cnt; j-- > 0;) {
+        const g2_jac p = in[first + j];
+        g2_aff a;
+        if (fp2_is_zero(p.z)) { fp2_zero(a.x); fp2_zero(a.y); a.inf = 1; }
+        else {
+            fp nz, t1, ni;
+            fp_sqr(nz, p.z.c0);
+            fp_sqr(t1, p.z.c1);
+            fp_add(nz, nz, t1);
+            fp_mul(ni, inv, pre[j]);                      // 1 / N(z)
+            fp_mul(inv, inv, nz);
+            fp2 zi, zi2;
+            fp_mul(zi.c0, p.z.c0, ni);
+            fp_mul(t1, p.z.c1, ni);
+            fp_neg(zi.c1, t1);                            // 1 / z = conj(z) / N(z)
+            fp2_sqr(zi2, zi);
+            fp2_mul(a.x, p.x, zi2);
+            fp2_mul(zi2, zi2, zi);
+            fp2_mul(a.y, p.y, zi2);
+            a.inf = 0;
+        }
+        out[first + j] = a;
+    }
 }
 __global__ void __launch_bounds__(B3_TPB) k_g1_aff_to_wire(const g1_aff* in, size_t n, uint8_t* out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -538,10 +775,13 @@ __global__ void __launch_bounds__(B3_TPB) k_g1_jac_to_pp(const g1_jac* in, size_
     out[i] = r;
 }
 // P_j = [c_j] apk_j straight into pairing form
-__global__ void __launch_bounds__(B3_TPB) k_g1_mul_u64_pp(const g1_jac* in, const uint64_t* __restrict__ k, size_t n, g1_pp* out) {
+// zero_flag: set when a scalar is 0 -- the reference's draw rule never yields 0 (M/src/aggregates.rs:280-286), and a zero scalar
+// would drop its set from the batch equation, so the call is rejected (B3_ERR_ARG)
+__global__ void __launch_bounds__(B3_TPB) k_g1_mul_u64_pp(const g1_jac* in, const uint64_t* __restrict__ k, size_t n, g1_pp* out, int32_t* zero_flag) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     g1_jac p = in[i], r;
+    if (k[i] == 0) *zero_flag = 1;
     pt_mul_u64_w4(r, p, k[i]);
     g1_pp o;
     g1_pp_from_jac(o, r);
@@ -819,69 +1059,8 @@ __global__ void __launch_bounds__(B3_COOP_THREADS) k_items_finish(const fp2* __r
     if (tid == 0) { accept[i] = fp12_is_one(s.rr) ? 1 : 0; status[i] = 0; }
 }
 
-// The same work with ONE THREAD per item (large batches): the thread folds its item's 2 x 68 lines into its own Fp12 with
-// shared squarings (dot-product sparse multiplications, tower.cuh) and runs the single-thread final exponentiation
-// (Karatsuba tower, Granger-Scott cyclotomic squarings: ~16.5 k Fp multiplications per item against ~2.5x that on the
-// cooperative path).  A CTA per item keeps at most 2 x 148 items in flight; a thread per item keeps every item of the
-// batch in flight, so the call is bound by one item's latency (batches up to ~19 k items) instead of by n / 296 of them.
-#define B3_ITEMS_TPB 32
-__device__ __noinline__ void item_fold_line(fp12*& f, fp12*& g, bool& have, const fp2* __restrict__ src, const fp& ny, const fp& z3, const fp& xz) {
-    fp2 l0 = src[0], l3 = src[1], l5 = src[2];
-    fp2_mul_fp(l0, l0, ny);
-    fp2_mul_fp(l3, l3, z3);
-    fp2_mul_fp(l5, l5, xz);
-    if (have) {
-        line_ops o;
-        line_ops_make(o, l0, l3, l5);
-        fp12_mul_by_line_dot(*g, *f, o);
-        fp12* t = f; f = g; g = t;
-    } else {
-        fp12_from_line(*f, l0, l3, l5);
-        have = true;
-    }
-}
-__global__ void __launch_bounds__(B3_ITEMS_TPB) k_items_finish_t(const fp2* __restrict__ lines, const uint32_t* __restrict__ qinf,
-                                                                  const g1_pp* __restrict__ keys, size_t n, const int32_t* st_sig,
-                                                                  const int32_t* st_key, const int32_t* sig_ok, int reject_inf_key,
-                                                                  int32_t* accept, int32_t* status, uint8_t* gt_wire) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int code = st_sig[i] ? st_sig[i] : st_key[i];
-    const g1_pp key = keys[i];
-    if (code != 0 || !sig_ok[i] || (reject_inf_key && key.inf)) {
-        accept[i] = 0; status[i] = code;
-        if (gt_wire) for (int b = 0; b < 576; b++) gt_wire[576 * i + b] = 0;
-        return;
-    }
-    const bool valid0 = !qinf[i], valid1 = !(qinf[n + i] || key.inf);
-    const fp gy = G1_GEN_Y, one = FP_ONE, gx = G1_GEN_X;           // pair 0 = (sig_i, -G1): -(-y) = y
-    fp12 buf[2];
-    fp12 *f = &buf[0], *g = &buf[1];
-    bool have = false;
-    const uint64_t x = B3_X_ABS;
-    const size_t np = 2 * n;
-    int a = B3_MILLER_DBL_SLOTS;
-#pragma unroll 1
-    for (int it = 0; it < B3_MILLER_DBL_SLOTS; it++) {
-        if (have) fp12_sqr(*f, *f);
-        const bool add = (x >> (62 - it)) & 1;
-#pragma unroll 1
-        for (int s = 0; s < (add ? 2 : 1); s++) {
-            const size_t slot = s == 0 ? (size_t)it : (size_t)a;
-            if (valid0) item_fold_line(f, g, have, lines + (slot * np + i) * 3, gy, one, gx);
-            if (valid1) item_fold_line(f, g, have, lines + (slot * np + n + i) * 3, key.ny, key.z3, key.xz);
-        }
-        if (add) a++;
-    }
-    if (!have) fp12_one(*f);
-    fp12_conj(*f, *f);
-    final_exp(*g, *f);
-    if (gt_wire) fp12_to_wire(gt_wire + 576 * i, *g);
-    accept[i] = fp12_is_one(*g) ? 1 : 0;
-    status[i] = 0;
-}
-
-// ... and with a LANE PAIR per item (medium batches): the Fp6 / Fp12 tower and the final exponentiation are templates over the
+// The same work with a LANE PAIR per item (large batches): a CTA per item keeps at most 2 x 148 items in flight, a lane pair per item
+// keeps every item of the batch in flight.  The Fp6 / Fp12 tower and the final exponentiation are templates over the
 // Fp2 representation (tower.cuh, pairing.cuh), so the same chain runs with every Fp2 value split over two lanes (fp2h.cuh):
 // half the latency of the thread-per-item kernel and twice the threads.  Sparse products use the Karatsuba form
 // (fp12_mul_by_line: 14 Fp2 products, each 444 multiply-accumulates per lane).

@@ -1,0 +1,293 @@
+"""Parity at the two HEADLINE shapes and on the rows the first-round suite covered thinly (VERDICT r1 "next round" 1):
+
+  * C4 -- 8192 sets x 128 keys through `pk_off` (four-lane staged key aggregation feeding [c]apk, eight-segment bucket sum,
+    14 accumulation chunks): every aggregate key against the C oracle, accept on the valid batch, and after ONE tampered message
+    first_bad == -1, reject, and GT bytes equal to (a) that set verified alone with its scalar (the final exponentiation is a
+    homomorphism and every valid set contributes one) and (b) the C oracle's verify_multiple over a 256-set slice.
+    The same batch through the device-resident key table (u32 indices) and through the two-phase entry gives the same bytes.
+  * subgroup checks -- 1000 random on-curve NON-members and members of G1 and of G2 (random points of the curve, points of the
+    cofactor torsion, member + torsion) against the oracle's full-length [r]P ladders (oracle/bls_oracle_c.c:386-387).
+  * invalid-curve inputs -- an off-curve key inside a multi-key set is rejected by every aggregating entry, and a zero
+    batch scalar is rejected at the C ABI.
+The C5 shape (the same call sharded over N > 1 NCCL ranks) is in tests/test_gpu_multirank.py.
+"""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import bls_oracle as O
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+ONE = O.f12_to_bytes(O.F12_ONE)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import __graft_entry__ as g
+    g.build_cuda()
+    import milagro_bls_b200 as mb
+    e = mb.Engine(0)
+    mb.set_default_engine(e)
+    return e
+
+
+def g1w(P):
+    return O.serialize_uncompressed_g1(P)
+
+
+def g2w(P):
+    return O.serialize_uncompressed_g2(P)
+
+
+@pytest.fixture(scope="module")
+def c4(eng):
+    """The C4 batch: 8192 sets x 128 keys drawn from a pool of 4096 validators; signing-side work on the GPU helpers
+    (spot-checked against the oracle below)."""
+    rnd = random.Random(0xC4)
+    n, nk, pool_n = 8192, 128, 4096
+    sks = [rnd.randrange(1, O.r) for _ in range(pool_n)]
+    pool = eng.g1_mul_gen(sks)
+    assert pool[77].tobytes() == g1w(O.sk_to_pk(sks[77]))
+    rs = np.random.RandomState(4)
+    idx = np.stack([rs.choice(pool_n, size=nk, replace=False) for _ in range(n)]).astype(np.uint32)
+    msgs = rs.randint(0, 256, size=(n, 32), dtype=np.uint8)
+    msgs[:, :4] = np.arange(n, dtype=">u4").view(np.uint8).reshape(n, 4)
+    agg_sk = [sum(sks[i] for i in row) % O.r for row in idx]
+    H = eng.hash_to_g2([m.tobytes() for m in msgs])
+    sigs = eng.g2_mul(H.reshape(-1), agg_sk)
+    assert sigs[5].tobytes() == g2w(O.g2_mul(O.hash_to_curve_g2(msgs[5].tobytes()), agg_sk[5]))
+    scalars = np.array([rnd.randrange(1, 1 << 63) for _ in range(n)], dtype=np.uint64)
+    return {"n": n, "nk": nk, "pool": pool, "idx": idx, "pks": np.ascontiguousarray(pool[idx.reshape(-1)]).reshape(-1),
+            "pk_off": np.arange(0, n * nk + 1, nk, dtype=np.uint32), "msgs": msgs, "moff": np.arange(0, 32 * n + 1, 32, dtype=np.uint32),
+            "sigs": np.ascontiguousarray(sigs).reshape(-1), "scalars": scalars, "sks": sks}
+
+
+def test_c4_key_aggregation_vs_c_oracle(eng, c4):
+    """All 8192 x 128 keys through the staged four-lane kernel; every aggregate against oc_g1_aggregate."""
+    out, st = eng.g1_aggregate(c4["pks"], c4["pk_off"])
+    assert not st.any()
+    nk = c4["nk"]
+    for j in range(c4["n"]):
+        rc, want = c_oracle.g1_aggregate(c4["pks"][96 * nk * j:96 * nk * (j + 1)])
+        assert rc == 0 and out[96 * j:96 * j + 96].tobytes() == want, j
+
+
+def test_c4_verify_multiple_parity(eng, c4):
+    n, nk, bad = c4["n"], c4["nk"], 5003
+    args = (c4["sigs"], c4["pks"], c4["pk_off"])
+    blob = c4["msgs"].reshape(-1)
+    ok, fb, gt = eng.verify_multiple(*args, blob, c4["moff"], c4["scalars"], want_gt=True)
+    assert ok and fb == -1 and gt == ONE
+    tam = c4["msgs"].copy()
+    tam[bad, 9] ^= 0x40
+    ok, fb, gt = eng.verify_multiple(*args, tam.reshape(-1), c4["moff"], c4["scalars"], want_gt=True)
+    assert not ok and fb == -1 and gt != ONE
+    # (a) the tampered set alone, same scalar (128 keys through pk_off)
+    one = lambda a, w: a[w * bad:w * (bad + 1)]
+    ok1, fb1, gt1 = eng.verify_multiple(one(c4["sigs"], 192), one(c4["pks"], 96 * nk), [0, nk], tam[bad], [0, 32],
+                                        c4["scalars"][bad:bad + 1], want_gt=True)
+    assert not ok1 and gt1 == gt
+    # (b) the C oracle on a 256-set slice around it (the reference's per-set algorithm, 128 keys per set)
+    lo, hi = bad - 100, bad + 156
+    ok_c, gt_c = c_oracle.verify_multiple(c4["sigs"][192 * lo:192 * hi], c4["pks"][96 * nk * lo:96 * nk * hi],
+                                          np.arange(0, nk * (hi - lo) + 1, nk, dtype=np.uint32), tam[lo:hi].reshape(-1),
+                                          np.arange(0, 32 * (hi - lo) + 1, 32, dtype=np.uint32), c4["scalars"][lo:hi])
+    assert not ok_c and gt_c == gt
+    # a non-subgroup signature deep in the batch: its index comes back, nothing else changes
+    sig_bad = c4["sigs"].copy()
+    sig_bad[192 * 7000:192 * 7001] = np.frombuffer(g2w(O.map_to_curve_g2((5, 7))), dtype=np.uint8)
+    ok, fb = eng.verify_multiple(sig_bad, c4["pks"], c4["pk_off"], blob, c4["moff"], c4["scalars"])
+    assert not ok and fb == 7000
+
+
+def test_c4_key_table_and_two_phase_match_byte_entry(eng, c4):
+    """The device-resident key table (loaded once from COMPRESSED keys, validated) + u32 indices, and the two-phase entry
+    (b3_sig_precheck -> b3_verify_multiple_checked), give the bytes of the byte-array entry."""
+    import milagro_bls_b200 as mb
+    comp, st = eng.g1_compress(c4["pool"].reshape(-1))
+    assert not st.any()
+    tbl = mb.KeyTable(eng)
+    first, st = tbl.append(comp, compressed=True, validate=True)
+    assert first == 0 and not st.any() and len(tbl) == len(c4["pool"])
+    back, st = tbl.get(np.arange(len(c4["pool"]), dtype=np.uint32))
+    assert not st.any() and back.tobytes() == c4["pool"].tobytes()
+    kidx = c4["idx"].reshape(-1)
+    agg_i, st = eng.g1_aggregate_indexed(tbl, kidx, c4["pk_off"])
+    agg_b, st2 = eng.g1_aggregate(c4["pks"], c4["pk_off"])
+    assert not st.any() and agg_i.tobytes() == agg_b.tobytes()
+    tam = c4["msgs"].copy()
+    tam[123, 31] ^= 1
+    for msgs in (c4["msgs"], tam):
+        ref = eng.verify_multiple(c4["sigs"], c4["pks"], c4["pk_off"], msgs.reshape(-1), c4["moff"], c4["scalars"], want_gt=True)
+        got = eng.verify_multiple_indexed(tbl, c4["sigs"], kidx, c4["pk_off"], msgs.reshape(-1), c4["moff"], c4["scalars"], want_gt=True)
+        assert got == ref
+        assert eng.sig_precheck(c4["sigs"]) == -1
+        ok, gt = eng.verify_multiple_checked(c4["pks"], c4["pk_off"], msgs.reshape(-1), c4["moff"], c4["scalars"], want_gt=True)
+        assert (ok, gt) == (ref[0], ref[2])
+        assert eng.sig_precheck(c4["sigs"]) == -1
+        got = eng.verify_multiple_indexed(tbl, None, kidx, c4["pk_off"], msgs.reshape(-1), c4["moff"], c4["scalars"], want_gt=True)
+        assert got == ref
+    # a *_checked call without its precheck is refused
+    with pytest.raises(RuntimeError):
+        eng.verify_multiple_checked(c4["pks"], c4["pk_off"], c4["msgs"].reshape(-1), c4["moff"], c4["scalars"])
+    # invalid table entries: rejected at load, and every set naming them fails
+    bad_keys = bytes([0x80]) + bytes(47) + g1_compress_of((0, 2))
+    first, st = tbl.append(bad_keys + comp[:48].tobytes(), compressed=True, validate=True)
+    assert list(st) == [-5, -5, 0]
+    with pytest.raises(mb.AmclError):
+        eng.verify_multiple_indexed(tbl, c4["sigs"][:192], np.array([first], dtype=np.uint32), None, c4["msgs"][0], [0, 32], c4["scalars"][:1])
+    with pytest.raises(mb.AmclError):        # index beyond the table
+        eng.verify_multiple_indexed(tbl, c4["sigs"][:192], np.array([len(tbl) + 5], dtype=np.uint32), None, c4["msgs"][0], [0, 32], c4["scalars"][:1])
+    tbl.close()
+
+
+def g1_compress_of(P):
+    """48-byte compressed encoding of an on-curve point that is NOT in G1 ((0, 2): 2^2 = 0 + 4)."""
+    return O.serialize_g1(P)
+
+
+def _rand_g1_point(rnd):
+    while True:
+        x = rnd.randrange(O.p)
+        rhs = (x * x * x + 4) % O.p
+        if O.fp_is_qr(rhs):
+            y = O.fp_sqrt(rhs)
+            return (x, y if rnd.getrandbits(1) else O.p - y)
+
+
+def _rand_g2_point(rnd):
+    while True:
+        x = (rnd.randrange(O.p), rnd.randrange(O.p))
+        sq, y = O.f2_sqrt(O.g2_rhs(x))
+        if sq and O.f2_sqr(y) == O.g2_rhs(x):
+            return (x, y if rnd.getrandbits(1) else O.f2_neg(y))
+
+
+def test_subgroup_checks_random_members_and_non_members(eng):
+    rnd = random.Random(2718)
+    # ---- G1: key_validate = on curve, not infinity, in G1 (phi-based test on the device, [r]P ladder in the oracle)
+    pts, want = [], []
+    for t in range(1000):
+        kind = t % 4
+        if kind == 0:
+            P = O.g1_mul(O.G1_GEN, rnd.randrange(1, O.r))                    # member
+        elif kind == 1:
+            P = _rand_g1_point(rnd)                                         # random point of the curve
+        elif kind == 2:
+            P = O.g1_mul(_rand_g1_point(rnd), O.r)                          # cofactor torsion (order divides h1)
+        else:
+            P = O.g1_add(O.g1_mul(O.G1_GEN, rnd.randrange(1, O.r)), O.g1_mul(_rand_g1_point(rnd), O.r))      # member + torsion
+        pts.append(g1w(P))
+        want.append(c_oracle.subgroup_check_g1(pts[-1]) and P is not None)
+    assert 200 <= sum(want) <= 300                                           # the members, and (almost surely) nothing else
+    st, ok = eng.g1_validate(b"".join(pts))
+    assert not st.any() and [bool(v) for v in ok] == want
+    # ---- G2: subgroup_check_g2 (psi-based test on the device)
+    pts, want = [], []
+    for t in range(1000):
+        kind = t % 4
+        if kind == 0:
+            P = O.g2_mul(O.G2_GEN, rnd.randrange(1, O.r))
+        elif kind == 1:
+            P = _rand_g2_point(rnd)
+        elif kind == 2:
+            P = O.g2_mul(_rand_g2_point(rnd), O.r)
+        else:
+            P = O.g2_add(O.g2_mul(O.G2_GEN, rnd.randrange(1, O.r)), O.g2_mul(_rand_g2_point(rnd), O.r))
+        pts.append(g2w(P))
+        want.append(c_oracle.subgroup_check_g2(pts[-1]))
+    assert 200 <= sum(want) <= 300
+    st, ok = eng.g2_subgroup_check(b"".join(pts))
+    assert not st.any() and [bool(v) for v in ok] == want
+
+
+def test_off_curve_key_rejected_by_every_aggregating_entry(eng):
+    """(1, 3): 9 != 1 + 4, not on the curve.  The reference cannot hold such a key (every PublicKey constructor checks)."""
+    import milagro_bls_b200 as mb
+    from milagro_bls_b200 import _lib
+    off_curve = (1).to_bytes(48, "big") + (3).to_bytes(48, "big")
+    sks = [11, 22, 33]
+    pks = [O.sk_to_pk(s) for s in sks]
+    msg = b"off-curve"
+    sig = g2w(O.aggregate_signatures([O.sign(s, msg) for s in sks]))
+    good = b"".join(g1w(P) for P in pks)
+    assert eng.fast_aggregate_verify(sig, good, msg)
+    evil = g1w(pks[0]) + off_curve + g1w(pks[2])
+    st, _ = eng.g1_validate(off_curve)
+    assert st[0] == -5
+    with pytest.raises(mb.AmclError):
+        eng.fast_aggregate_verify(sig, evil, msg)
+    out, st = eng.g1_aggregate(evil, [0, 3])
+    assert st[0] == -5
+    with pytest.raises(mb.AmclError):
+        eng.verify_multiple(sig, evil, [0, 3], msg, [0, len(msg)], np.array([5], dtype=np.uint64))
+    acc, st = eng.verify_batch(_lib.ITEM_FAST_AGGREGATE, sig, evil, [0, 3], [msg])
+    assert not acc[0] and st[0] == -5
+    # an off-curve G2 point in a signature aggregate
+    evil2 = g2w(O.G2_GEN) + (b"\x00" * 47 + b"\x01") * 4
+    out, st = eng.g2_aggregate(evil2, [0, 2])
+    assert st[0] == -5
+    # trusted mode (the caller vouches for its points) skips the check: documented, opt-in
+    eng.set_trusted_points(True)
+    out, st = eng.g1_aggregate(good, [0, 3])
+    eng.set_trusted_points(False)
+    assert st[0] == 0 and out.tobytes() == g1w(O.aggregate_public_keys(pks))
+
+
+def test_zero_scalar_rejected(eng):
+    """A zero batch scalar would drop its set from the equation (a forged signature in it would pass); the reference's draw
+    rule never yields it (M/src/aggregates.rs:280-286), so the C ABI refuses it -- host-pointer and device-pointer entries."""
+    import torch
+    import milagro_bls_b200 as mb
+    sks = [5, 6]
+    msgs = [b"m0" * 16, b"m1" * 16]
+    sigs = g2w(O.sign(sks[0], msgs[0])) + g2w(O.sign(sks[1], b"forged" * 4))      # second signature is NOT for msgs[1]
+    pks = g1w(O.sk_to_pk(sks[0])) + g1w(O.sk_to_pk(sks[1]))
+    ok, fb = eng.verify_multiple(sigs, pks, None, b"".join(msgs), [0, 32, 64], np.array([3, 9], dtype=np.uint64))
+    assert not ok
+    with pytest.raises(RuntimeError):
+        eng.verify_multiple(sigs, pks, None, b"".join(msgs), [0, 32, 64], np.array([3, 0], dtype=np.uint64))
+    dev = torch.device("cuda", 0)
+    d = [torch.from_numpy(np.frombuffer(x, dtype=np.uint8).copy()).to(dev) for x in (sigs, pks, b"".join(msgs))]
+    moff = torch.tensor([0, 32, 64], dtype=torch.int32, device=dev)
+    sc = torch.tensor([3, 0], dtype=torch.int64, device=dev)
+    part = torch.zeros(mb._lib.PARTIAL_BYTES, dtype=torch.uint8, device=dev)
+    with pytest.raises(RuntimeError):
+        eng.verify_multiple_partial_dev(d[0].data_ptr(), d[1].data_ptr(), None, d[2].data_ptr(), moff.data_ptr(), sc.data_ptr(), 2, 0, part.data_ptr())
+
+
+def test_python_layer_rejects_short_buffers(eng):
+    import milagro_bls_b200 as mb
+    with pytest.raises(ValueError):
+        mb.PublicKey(b"")
+    with pytest.raises(ValueError):
+        mb.Signature(b"\x00" * 96)
+    with pytest.raises(ValueError):
+        eng.verify(b"\x00" * 10, b"\x00" * 96, b"m")
+    with pytest.raises(ValueError):
+        eng.verify_multiple(b"\x00" * 192, b"\x00" * 96, None, b"abc", [0, 5], np.array([1], dtype=np.uint64))
+    with pytest.raises(ValueError):
+        eng.g1_aggregate(b"\x00" * 96, [0, 2])
+
+
+def test_batch_normalisation_matches_oracle(eng):
+    """Montgomery-trick normalisation (several points per inversion, chunk sizes 1..16 by batch size): hash_to_G2 outputs of
+    a 40000-message batch, spot-checked against the oracle, and an aggregate batch with infinities inside the chunks."""
+    rnd = random.Random(5)
+    msgs = [rnd.getrandbits(64).to_bytes(8, "big") + bytes([j & 255]) * (j % 40) for j in range(40000)]
+    H = eng.hash_to_g2(msgs)
+    for j in (0, 1, 2, 17, 12345, 39998, 39999):
+        assert H[j].tobytes() == g2w(O.hash_to_curve_g2(msgs[j])), j
+    P = O.sk_to_pk(123)
+    sets = [[P, O.g1_neg(P)] if j % 3 == 0 else [P] * (1 + j % 4) for j in range(50000)]
+    off = np.cumsum([0] + [len(s) for s in sets]).astype(np.uint32)
+    w, wn = np.frombuffer(g1w(P), dtype=np.uint8), np.frombuffer(g1w(O.g1_neg(P)), dtype=np.uint8)
+    blob = np.concatenate([np.concatenate([w, wn]) if j % 3 == 0 else np.tile(w, 1 + j % 4) for j in range(50000)])
+    out, st = eng.g1_aggregate(blob, off)
+    assert not st.any()
+    want = {k: g1w(O.g1_mul(P, k)) for k in (1, 2, 3, 4)}
+    for j in range(0, 50000, 997):
+        exp = g1w(None) if j % 3 == 0 else want[1 + j % 4]
+        assert out[96 * j:96 * j + 96].tobytes() == exp, j

@@ -599,7 +599,7 @@ def test_verify_multiple_sharded_host_partials(eng):
             assert not ok and fb == 3                                   # global index of the non-subgroup signature
 
 
-@pytest.fixture(params=[1, 2, 3], ids=["cta_per_item", "thread_per_item", "lane_pair_per_item"])
+@pytest.fixture(params=[1, 3], ids=["cta_per_item", "lane_pair_per_item"])
 def item_kernel(eng, request):
     """All three finishing kernels of b3_verify_batch on the same small batches (the default picks by batch size)."""
     eng.set_item_kernel(request.param)
