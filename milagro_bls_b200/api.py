@@ -203,6 +203,21 @@ class Engine:
         self._ck(self.L.b3_hash_to_g2(self.handle, p, off.ctypes.data, n, dp, dl, out.ctypes.data))
         return out[:192 * n].reshape(n, 192)
 
+    def hash_to_g2_blob(self, msgs_blob, msg_offsets, dst=None):
+        """hash_to_g2 over a packed message blob + n + 1 offsets (no per-message Python objects)."""
+        off = _u32(msg_offsets)
+        n = len(off) - 1
+        _need(n >= 0 and (n == 0 or (off[0] == 0 and int(off[-1]) == len(msgs_blob))), "hash_to_g2_blob: offsets must be n + 1 values ending at len(msgs)")
+        p, keep = _buf(msgs_blob)
+        out = np.zeros(192 * max(n, 1), dtype=np.uint8)
+        if dst is None:
+            dp, dl, keep2 = None, 0, None
+        else:
+            dp, keep2 = _buf(dst)
+            dl = len(dst)
+        self._ck(self.L.b3_hash_to_g2(self.handle, p, off.ctypes.data, n, dp, dl, out.ctypes.data))
+        return out[:192 * n].reshape(n, 192)
+
     def verify(self, sig192, pk96, msg, want_gt=False):
         _need(len(sig192) == 192 and len(pk96) == 96, "verify: signature must be 192 bytes and the key 96 bytes (uncompressed)")
         ok = ctypes.c_int(0)

@@ -5,6 +5,7 @@ instances of verify_multiple_aggregate_signatures on disjoint chunks of the same
 kind = "port": the Rust crate cannot be compiled in this image (no rustc/cargo), so this is the oracle port, built
 with gcc -O3 -march=native.  TEST / MEASUREMENT INFRASTRUCTURE ONLY -- never on the product path.
 """
+import ctypes
 import os
 import threading
 import time
@@ -69,6 +70,33 @@ def run(n_sets, n_keys, seed=0xB200, threads=None):
     sec = time.perf_counter() - t0
     assert all(results), "CPU baseline: the valid synthetic batch must verify"
     return {"sets": n_sets, "seconds": sec, "threads": threads, "kind": "port"}
+
+
+def run_hash_to_g2(n_msgs, threads=None, seed=0xB200):
+    """Second headline metric on the CPU: hash_to_curve_g2 (A/bls381/core.rs:831-849) of n_msgs distinct 32-byte messages,
+    T independent single-threaded instances on disjoint chunks."""
+    threads = threads or os.cpu_count() or 1
+    threads = max(1, min(threads, n_msgs))
+    rs = np.random.RandomState(seed & 0x7fffffff)
+    msgs = [rs.bytes(32) for _ in range(n_msgs)]
+    L = c_oracle.lib()
+    out = [np.zeros(192, dtype=np.uint8) for _ in range(threads)]
+
+    def work(t):
+        o = out[t]
+        for i in range(t, n_msgs, threads):
+            m = np.frombuffer(msgs[i], dtype=np.uint8)
+            L.oc_hash_to_g2(c_oracle._p(m), ctypes.c_size_t(32), None, ctypes.c_size_t(0), c_oracle._p(o))      # releases the GIL
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    sec = time.perf_counter() - t0
+    assert out[0].any()
+    return {"msgs": n_msgs, "seconds": sec, "threads": threads, "kind": "port"}
 
 
 if __name__ == "__main__":

@@ -16,7 +16,9 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 eng = mb.Engine(0)
-lane = bench.Lane(0, dev, n, 128, 0xB200, 0, 0)
+bench.POOL = 16384                       # a small validator pool is enough for kernel captures
+sks, pool = bench.synth_pool(eng, 0xB200)
+lane = bench.Lane(0, dev, None, sks, pool, n, 128, 0xB200, 0, 0, 0)
 part = torch.zeros(mb._lib.PARTIAL_BYTES, dtype=torch.uint8, device=dev)
 torch.cuda.synchronize()
 for _ in range(steps):
