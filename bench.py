@@ -95,7 +95,13 @@ def synth_inputs(eng, sks, pool, n_sets, n_keys, seed, rank=0):
     (GPU helper b3_g2_mul; input synthesis, not timed)."""
     import numpy as np
     rs = np.random.RandomState((seed + 7919 * rank) & 0x7fffffff)
-    idx = np.stack([rs.choice(POOL, size=n_keys, replace=False) for _ in range(n_sets)]).astype(np.uint32)      # (n_sets, n_keys)
+    idx = rs.randint(0, POOL, size=(n_sets, n_keys)).astype(np.uint32)                         # (n_sets, n_keys), distinct within a set:
+    while True:
+        srt = np.sort(idx, axis=1)
+        dup = np.nonzero((srt[:, 1:] == srt[:, :-1]).any(axis=1))[0]
+        if len(dup) == 0:
+            break
+        idx[dup] = rs.randint(0, POOL, size=(len(dup), n_keys)).astype(np.uint32)
     msgs = rs.randint(0, 256, size=(n_sets, MSG_LEN), dtype=np.uint8)
     msgs[:, 0] = rank
     msgs[:, 1:5] = np.arange(n_sets, dtype=">u4").view(np.uint8).reshape(n_sets, 4)            # all distinct
