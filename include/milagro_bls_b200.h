@@ -65,6 +65,10 @@ void b3_ctx_set_item_kernel(b3_ctx* ctx, int which);
  * point arrays passed to this context come out of this library's own decompress / validate / aggregate calls (the
  * reference's type invariant) and skips that check.  Default 0. */
 void b3_ctx_set_trusted_points(b3_ctx* ctx, int trusted);
+/* Chain kernels of a verify_multiple call (subgroup checks, [c]apk, Miller point chains): 0 (default) = the replicated-lane
+ * form -- twice the lanes per item, lower latency, ~25 % more arithmetic -- when the call is the only one in flight on its
+ * device and has at most 16384 sets, the plain form otherwise; 1 = always replicated; 2 = always plain. */
+void b3_ctx_set_latency_mode(b3_ctx* ctx, int mode);
 int b3_stage_count(void);
 
 /* ---- (de)serialisation: PublicKey::{from_bytes, from_bytes_unchecked, as_bytes} (M/src/keys.rs:140-160),

@@ -50,6 +50,7 @@ def lib():
         "b3_ctx_set_serial": ([vp, ctypes.c_int], None),
         "b3_ctx_set_item_kernel": ([vp, ctypes.c_int], None),
         "b3_ctx_set_trusted_points": ([vp, ctypes.c_int], None),
+        "b3_ctx_set_latency_mode": ([vp, ctypes.c_int], None),
         "b3_g1_decompress": ([vp, u8p, sz, ctypes.c_int, u8p, i32p], ctypes.c_int),
         "b3_g2_decompress": ([vp, u8p, sz, u8p, i32p], ctypes.c_int),
         "b3_g1_compress": ([vp, u8p, sz, u8p, i32p], ctypes.c_int),

@@ -339,6 +339,10 @@ class Engine:
                                                 st.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
         return out[:96 * n], st[:n]
 
+    def set_latency_mode(self, mode=0):
+        """Chain kernels of verify_multiple: 0 = replicated lanes when the call is alone on its GPU (default), 1 = always, 2 = never."""
+        self.L.b3_ctx_set_latency_mode(self.handle, int(mode))
+
     def set_trusted_points(self, trusted=True):
         """trusted=True: the point arrays passed to this context come out of this library's own decompress / validate calls
         (the reference's type invariant), so the aggregation kernels skip their on-curve checks."""

@@ -53,6 +53,8 @@ struct b3_ctx {
     cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_fork2 = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
     int serial = 0;
+    int latency_mode = 0;           // chain kernels: 0 = replicated lanes (quad.cuh) when this is the only call in flight on the device, 1 = always, 2 = never
+    bool wide_now = false;          // decision for the call being enqueued
     int trusted = 0;                // 1: key / signature arrays come from the library's own validated outputs: skip the on-curve checks of the aggregation kernels
     int item_kernel = 0;            // b3_verify_batch finishing kernel: 0 = by batch size, 1 = CTA per item, 3 = lane pair per item
     // scratch (grown on demand, reused across calls)
@@ -177,6 +179,20 @@ extern "C" int b3_stage_count(void) { return B3_N_STAGES - 1; }
 extern "C" void b3_ctx_set_serial(b3_ctx* ctx, int serial) { if (ctx) ctx->serial = serial; }
 extern "C" void b3_ctx_set_item_kernel(b3_ctx* ctx, int which) { if (ctx) ctx->item_kernel = which; }
 extern "C" void b3_ctx_set_trusted_points(b3_ctx* ctx, int trusted) { if (ctx) ctx->trusted = trusted; }
+extern "C" void b3_ctx_set_latency_mode(b3_ctx* ctx, int mode) { if (ctx && mode >= 0 && mode <= 2) ctx->latency_mode = mode; }
+// verification calls in flight per device (all contexts of the process): a call that is alone on its GPU cannot fill it with
+// one item per set, so its chain kernels run in the replicated form (twice the lanes per item, ~25 % more arithmetic);
+// with several calls in flight the plain kernels give the higher throughput.
+#include <atomic>
+static std::atomic<int> g_calls_in_flight[64];
+struct call_guard {
+    b3_ctx* ctx;
+    explicit call_guard(b3_ctx* c, size_t n) : ctx(c) {
+        const int others = g_calls_in_flight[ctx->device & 63].fetch_add(1);
+        ctx->wide_now = ctx->latency_mode == 1 || (ctx->latency_mode == 0 && others == 0 && n <= 16384);
+    }
+    ~call_guard() { g_calls_in_flight[ctx->device & 63].fetch_sub(1); }
+};
 static void mark_reset(b3_ctx* ctx) { ctx->n_spans = 0; }
 // open a stage span on `strm`; returns the span index (or -1 when the table is full)
 static int span_begin(b3_ctx* ctx, int id, cudaStream_t strm) {
@@ -256,7 +272,10 @@ static int g2_sum(b3_ctx* ctx, g2_jac* a, g2_jac* b, size_t n, g2_jac** res, cud
 static int miller_lines(b3_ctx* ctx, cudaStream_t strm, const g2_jac* q, size_t n_pairs, size_t first, size_t count) {
     if (count == 0) return B3_OK;
     int sp = span_begin(ctx, ST_MILLER_LINES, strm);
-    LAUNCH_ON(strm, k_miller_lines, nblk(2 * count), B3_TPB, q, n_pairs, first, count, (fp2*)ctx->lines.p, (uint32_t*)ctx->qinf.p);
+    if (ctx->wide_now || count <= 64)          // few pairs (the window sums of the signature MSM): always latency-bound
+        LAUNCH_ON(strm, k_miller_lines_q, nblk(4 * count), B3_TPB, q, n_pairs, first, count, (fp2*)ctx->lines.p, (uint32_t*)ctx->qinf.p);
+    else
+        LAUNCH_ON(strm, k_miller_lines, nblk(2 * count), B3_TPB, q, n_pairs, first, count, (fp2*)ctx->lines.p, (uint32_t*)ctx->qinf.p);
     span_end(ctx, sp, strm);
     return B3_OK;
 }
@@ -988,8 +1007,10 @@ static int vm_stages(b3_ctx* ctx, const vm_in& in, size_t n_total, int32_t* d_st
         CK(cudaStreamWaitEvent(s3, ctx->ev_fork2, 0));
     }
     sp = span_begin(ctx, ST_SIG_CHECK, s0);
-    if (!in.prechecked)
-        LAUNCH_ON(s0, k_g2_subgroup, nblk(2 * n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, (const int32_t*)d_st_sig, n, (int32_t*)ctx->ok.p);
+    if (!in.prechecked) {
+        if (ctx->wide_now) LAUNCH_ON(s0, k_g2_subgroup_q, nblk(4 * n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, (const int32_t*)d_st_sig, n, (int32_t*)ctx->ok.p);
+        else LAUNCH_ON(s0, k_g2_subgroup, nblk(2 * n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, (const int32_t*)d_st_sig, n, (int32_t*)ctx->ok.p);
+    }
     LAUNCH_ON(s0, k_first_bad, nblk(n), B3_TPB, (const int32_t*)ctx->ok.p, n, in.index_base, d_first_bad);
     span_end(ctx, sp, s0);
     // 2. aggregate public keys; 3. P_j = [c_j] apk_j (M/src/aggregates.rs:293)
@@ -1008,7 +1029,8 @@ static int vm_stages(b3_ctx* ctx, const vm_in& in, size_t n_total, int32_t* d_st
     }
     span_end(ctx, sp, s1);
     sp = span_begin(ctx, ST_G1_MUL, s1);
-    LAUNCH_ON(s1, k_g1_mul_u64_pp, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j.p, in.d_scalars, n, p, d_zero);
+    if (ctx->wide_now) LAUNCH_ON(s1, k_g1_mul_u64_pp_d, nblk(2 * n), B3_TPB, (const g1_jac*)ctx->g1j.p, in.d_scalars, n, p, d_zero);
+    else LAUNCH_ON(s1, k_g1_mul_u64_pp, nblk(n), B3_TPB, (const g1_jac*)ctx->g1j.p, in.d_scalars, n, p, d_zero);
     span_end(ctx, sp, s1);
     // 5. S = sum_j [c_j] sig_j (M/src/aggregates.rs:303), on aux3: the context's own (highest-priority) stream is left to the
     //    end of the call
@@ -1225,12 +1247,14 @@ static int vm_begin(b3_ctx* ctx) {
     return B3_OK;
 }
 static int vm_whole(b3_ctx* ctx, const vm_in& in, int* accept, int64_t* first_bad, uint8_t* gt576) {
+    call_guard guard(ctx, in.n);
     fp12* res;
     long long* d_fb;
     CKR(vm_enqueue(ctx, in, &res, &d_fb));
     return vm_finish_whole(ctx, in.n, res, d_fb, accept, first_bad, gt576);
 }
 static int vm_partial(b3_ctx* ctx, const vm_in& in, uint8_t* partial_dev) {
+    call_guard guard(ctx, in.n);
     fp12* res;
     long long* d_fb;
     CKR(vm_enqueue(ctx, in, &res, &d_fb));

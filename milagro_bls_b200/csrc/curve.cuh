@@ -35,6 +35,19 @@ B3_FN void f_select(fp2& r, bool c, const fp2& a, const fp2& b) { fp2_select(r, 
 B3_FN void f_one(fp2& r) { fp2_one(r); }
 B3_FN void f_zero(fp2& r) { fp2_zero(r); }
 
+// ---- PAIRED products ------------------------------------------------------------------------------------------------
+// Two INDEPENDENT products of a formula, named as a pair.  For the one-thread (fp, fp2) and lane-pair (fp2h) representations
+// they simply run one after the other; the replicated representations of quad.cuh (fpd: an Fp value held by both lanes of a
+// lane pair, fp2q: a lane-pair Fp2 value held by both pairs of a lane quad) run them AT THE SAME TIME, one on each half of
+// the group, and exchange the results -- twice the threads per item for the latency-bound chains of a single call.
+// The point formulas below are ordered into such pairs.  No output may alias an input of the other product.
+template <class F>
+B3_FN void f_mul_par(F& r1, const F& a1, const F& b1, F& r2, const F& a2, const F& b2) { f_mul(r1, a1, b1); f_mul(r2, a2, b2); }
+template <class F>
+B3_FN void f_sqr_par(F& r1, const F& a1, F& r2, const F& a2) { f_sqr(r1, a1); f_sqr(r2, a2); }
+template <class F>
+B3_FN void f_mulsqr_par(F& r1, const F& a1, const F& b1, F& r2, const F& a2) { f_mul(r1, a1, b1); f_sqr(r2, a2); }
+
 // curve constant b: 4 (G1) / 4(1+i) (G2)
 B3_FN void f_mul_b(fp& r, const fp& a) { fp t; fp_dbl(t, a); fp_dbl(r, t); }
 B3_FN void f_mul_b(fp2& r, const fp2& a) { fp2 t; fp2_dbl(t, a); fp2_dbl(t, t); fp2_mul_xi(r, t); }
@@ -70,22 +83,20 @@ B3_FN void pt_select(jac<F>& r, bool c, const jac<F>& a, const jac<F>& b) {
 }
 
 // dbl-2009-l (a = 0): 2M + 5S.  Z = 0 stays Z = 0.  (Neither curve has 2-torsion, so Y != 0 on finite points.)
+// Paired: (X^2, Y^2), (B^2, (X+B)^2), (Y Z, E^2), E (D - X3): four rounds instead of seven products.
 template <class F>
 B3_FN_NOINLINE void pt_dbl(jac<F>& r, const jac<F>& p) {
-    F A, B, C, D, E, Fq, t;
-    f_sqr(A, p.x);
-    f_sqr(B, p.y);
-    f_sqr(C, B);
+    F A, B, C, D, E, Fq, t, yz;
+    f_sqr_par(A, p.x, B, p.y);
     f_add(t, p.x, B);
-    f_sqr(t, t);
-    f_sub(t, t, A);
-    f_sub(t, t, C);
-    f_dbl(D, t);
+    f_sqr_par(C, B, D, t);
+    f_sub(D, D, A);
+    f_sub(D, D, C);
+    f_dbl(D, D);
     f_dbl(E, A);
     f_add(E, E, A);
-    f_sqr(Fq, E);
-    f_mul(t, p.y, p.z);
-    f_dbl(r.z, t);
+    f_mulsqr_par(yz, p.y, p.z, Fq, E);
+    f_dbl(r.z, yz);
     f_dbl(t, D);
     f_sub(r.x, Fq, t);
     f_sub(t, D, r.x);
@@ -94,19 +105,15 @@ B3_FN_NOINLINE void pt_dbl(jac<F>& r, const jac<F>& p) {
     f_sub(r.y, t, C);
 }
 
-// add-2007-bl with explicit handling of infinity / doubling / inverse operands: 11M + 5S
+// add-2007-bl with explicit handling of infinity / doubling / inverse operands: 11M + 5S in eight paired rounds
 template <class F>
 B3_FN_NOINLINE void pt_add(jac<F>& r, const jac<F>& p, const jac<F>& q) {
     bool pinf = pt_is_inf(p), qinf = pt_is_inf(q);
-    F Z1Z1, Z2Z2, U1, U2, S1, S2, H, I, J, rr, V, t;
-    f_sqr(Z1Z1, p.z);
-    f_sqr(Z2Z2, q.z);
-    f_mul(U1, p.x, Z2Z2);
-    f_mul(U2, q.x, Z1Z1);
-    f_mul(t, q.z, Z2Z2);
-    f_mul(S1, p.y, t);
-    f_mul(t, p.z, Z1Z1);
-    f_mul(S2, q.y, t);
+    F Z1Z1, Z2Z2, U1, U2, S1, S2, H, I, J, rr, V, t, t2;
+    f_sqr_par(Z1Z1, p.z, Z2Z2, q.z);
+    f_mul_par(U1, p.x, Z2Z2, U2, q.x, Z1Z1);
+    f_mul_par(t, q.z, Z2Z2, t2, p.z, Z1Z1);
+    f_mul_par(S1, p.y, t, S2, q.y, t2);
     f_sub(H, U2, U1);
     f_sub(rr, S2, S1);
     if (!pinf && !qinf && f_is_zero(H) && f_is_zero(rr)) {      // P == Q
@@ -116,37 +123,32 @@ B3_FN_NOINLINE void pt_add(jac<F>& r, const jac<F>& p, const jac<F>& q) {
     jac<F> o;
     f_dbl(rr, rr);
     f_dbl(I, H);
-    f_sqr(I, I);
-    f_mul(J, H, I);
-    f_mul(V, U1, I);
-    f_sqr(o.x, rr);
+    f_add(t, p.z, q.z);
+    f_sqr_par(I, I, t2, t);                                      // I = (2H)^2, t2 = (Z1 + Z2)^2
+    f_sub(t2, t2, Z1Z1);
+    f_sub(t2, t2, Z2Z2);
+    f_mul_par(J, H, I, V, U1, I);
+    f_mulsqr_par(S2, S1, J, o.x, rr);                            // S2 = S1 J, o.x = rr^2
     f_sub(o.x, o.x, J);
     f_dbl(t, V);
     f_sub(o.x, o.x, t);
     f_sub(t, V, o.x);
-    f_mul(t, rr, t);
-    f_mul(S1, S1, J);
-    f_dbl(S1, S1);
-    f_sub(o.y, t, S1);
-    f_add(t, p.z, q.z);
-    f_sqr(t, t);
-    f_sub(t, t, Z1Z1);
-    f_sub(t, t, Z2Z2);
-    f_mul(o.z, t, H);                                            // H == 0, r != 0  =>  Z3 = 0 (infinity)
+    f_mul_par(U2, rr, t, o.z, t2, H);                            // H == 0, r != 0  =>  Z3 = 0 (infinity)
+    f_dbl(S2, S2);
+    f_sub(o.y, U2, S2);
     pt_select(o, qinf, p, o);
     pt_select(r, pinf, q, o);
 }
 
-// madd-2007-bl (q affine, finite or flagged infinity): 7M + 4S
+// madd-2007-bl (q affine, finite or flagged infinity): 7M + 4S in six paired rounds
 template <class F>
 B3_FN_NOINLINE void pt_add_aff(jac<F>& r, const jac<F>& p, const aff<F>& q) {
     bool pinf = pt_is_inf(p), qinf = q.inf != 0;
-    F Z1Z1, U2, S2, H, HH, I, J, rr, V, t;
+    F Z1Z1, U2, S2, H, HH, I, J, rr, V, t, t2;
     f_sqr(Z1Z1, p.z);
-    f_mul(U2, q.x, Z1Z1);
-    f_mul(t, p.z, Z1Z1);
-    f_mul(S2, q.y, t);
+    f_mul_par(U2, q.x, Z1Z1, t, p.z, Z1Z1);
     f_sub(H, U2, p.x);
+    f_mulsqr_par(S2, q.y, t, HH, H);
     f_sub(rr, S2, p.y);
     if (!pinf && !qinf && f_is_zero(H) && f_is_zero(rr)) {
         pt_dbl(r, p);
@@ -154,23 +156,19 @@ B3_FN_NOINLINE void pt_add_aff(jac<F>& r, const jac<F>& p, const aff<F>& q) {
     }
     jac<F> o, qj;
     f_dbl(rr, rr);
-    f_sqr(HH, H);
     f_dbl(I, HH); f_dbl(I, I);
-    f_mul(J, H, I);
-    f_mul(V, p.x, I);
-    f_sqr(o.x, rr);
+    f_mul_par(J, H, I, V, p.x, I);
+    f_add(t, p.z, H);
+    f_sqr_par(o.x, rr, t2, t);                                   // o.x = rr^2, t2 = (Z1 + H)^2
     f_sub(o.x, o.x, J);
     f_dbl(t, V);
     f_sub(o.x, o.x, t);
     f_sub(t, V, o.x);
-    f_mul(t, rr, t);
-    f_mul(S2, p.y, J);
+    f_mul_par(U2, rr, t, S2, p.y, J);
     f_dbl(S2, S2);
-    f_sub(o.y, t, S2);
-    f_add(t, p.z, H);
-    f_sqr(t, t);
-    f_sub(t, t, Z1Z1);
-    f_sub(o.z, t, HH);
+    f_sub(o.y, U2, S2);
+    f_sub(t2, t2, Z1Z1);
+    f_sub(o.z, t2, HH);
     qj.x = q.x; qj.y = q.y; f_one(qj.z);
     pt_select(o, qinf, p, o);
     pt_select(r, pinf, qj, o);

@@ -5,6 +5,7 @@
 #include "pairing.cuh"
 #include "coop12.cuh"
 #include "fp2h.cuh"
+#include "quad.cuh"
 
 #define B3_ERR_AGGREGATE_EMPTY_POINTS_D (-1)
 #define B3_ERR_INVALID_G1_SIZE_D (-6)
@@ -55,6 +56,18 @@ __global__ void B3_LBH k_g2_subgroup(const g2_aff* pts, const int32_t* status, s
         good = g2_in_subgroup_aff(a) ? 1 : 0;
     }
     if (!pair_odd()) ok[i] = good;
+}
+// the same on LANE QUADS (quad.cuh): threads 4i .. 4i+3 work on signature i, paired products split over the two lane pairs
+__global__ void B3_LBH k_g2_subgroup_q(const g2_aff* pts, const int32_t* status, size_t n, int32_t* ok) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    if (i >= n) return;
+    int good = 0;
+    if (status[i] == B3_OK) {
+        g2q_aff a;
+        g2q_load(a, pts[i]);
+        good = g2_in_subgroup_aff(a) ? 1 : 0;
+    }
+    if ((threadIdx.x & 3u) == 0) ok[i] = good;
 }
 // key_validate on parsed G1 points (not infinity, in G1)
 __global__ void __launch_bounds__(B3_TPB) k_g1_key_validate(const g1_jac* pts, const int32_t* status, size_t n, int32_t* valid) {
@@ -787,6 +800,29 @@ __global__ void __launch_bounds__(B3_TPB) k_g1_mul_u64_pp(const g1_jac* in, cons
     g1_pp_from_jac(o, r);
     out[i] = o;
 }
+// the same on LANE PAIRS (quad.cuh: fpd): threads (2i, 2i+1) work on set i, the paired products of the point formulas split
+// over the two lanes
+__global__ void __launch_bounds__(B3_TPB) k_g1_mul_u64_pp_d(const g1_jac* in, const uint64_t* __restrict__ k, size_t n, g1_pp* out, int32_t* zero_flag) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    if (i >= n) return;
+    g1d_jac p, r;
+    g1d_load(p, in[i]);
+    const uint64_t c = k[i];
+    if (c == 0) *zero_flag = 1;
+    pt_mul_u64_w4(r, p, c);
+    // pairing form (X Z, -Y, Z^3): Z^2 and X Z as a pair, then Z^3
+    fpd z2, xz, z3;
+    f_mulsqr_par(xz, r.x, r.z, z2, r.z);
+    f_mul(z3, z2, r.z);
+    if (!pair_odd()) {
+        g1_pp o;
+        o.xz = xz.v;
+        fp_neg(o.ny, r.y.v);
+        o.z3 = z3.v;
+        o.inf = fp_is_zero(r.z.v) ? 1u : 0u;
+        out[i] = o;
+    }
+}
 // constant pair member: -G1 generator
 __global__ void k_set_neg_g1_pp(g1_pp* out) {
     g1_pp a;
@@ -833,6 +869,46 @@ __global__ void B3_LBH k_miller_lines(const g2_jac* __restrict__ q, size_t n, si
             miller_add_step_u(t, u0, l3, u5, Q.x, Q.y, Q.z);
             o = lines + ((size_t)a * n + i) * 3;
             fp2h_store(o[0], u0); fp2h_store(o[1], l3); fp2h_store(o[2], u5);
+            a++;
+        }
+    }
+}
+//    LANE QUADS (quad.cuh): threads 4i .. 4i+3 run the chain of pair i with the paired products of every step split over
+//    the two lane pairs; the low pair stores u0 and l3, the high pair u5.
+__global__ void B3_LBH k_miller_lines_q(const g2_jac* __restrict__ q, size_t n, size_t first, size_t count,
+                                        fp2* __restrict__ lines, uint32_t* __restrict__ qinf) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    if (i >= count) return;
+    i += first;
+    fp2q X, Y, Z;
+    fp2h_load(X, q[i].x);
+    fp2h_load(Y, q[i].y);
+    fp2h_load(Z, q[i].z);
+    const bool inf = fp2_is_zero(Z);
+    if ((threadIdx.x & 3u) == 0) qinf[i] = inf ? 1u : 0u;
+    if (inf) return;                           // its lines are never read: the accumulate kernel skips the pair
+    miller_pt_t<fp2q> t, Q;
+    {                                          // homogeneous (X Z : Y : Z^3)
+        fp2q z2;
+        f_mulsqr_par(t.x, X, Z, z2, Z);
+        t.y = Y;
+        f_mul(t.z, z2, Z);
+    }
+    Q = t;
+    const uint64_t x = B3_X_ABS;
+    const bool hi = quad_hi();
+    int a = B3_MILLER_DBL_SLOTS;
+    fp2q u0, l3, u5;
+    for (int it = 0; it < B3_MILLER_DBL_SLOTS; it++) {
+        miller_dbl_step_u(t, u0, l3, u5);
+        fp2* o = lines + ((size_t)it * n + i) * 3;
+        if (hi) fp2h_store(o[2], u5);
+        else { fp2h_store(o[0], u0); fp2h_store(o[1], l3); }
+        if ((x >> (62 - it)) & 1) {
+            miller_add_step_u(t, u0, l3, u5, Q.x, Q.y, Q.z);
+            o = lines + ((size_t)a * n + i) * 3;
+            if (hi) fp2h_store(o[2], u5);
+            else { fp2h_store(o[0], u0); fp2h_store(o[1], l3); }
             a++;
         }
     }

@@ -101,31 +101,29 @@ struct miller_pt_t {
 };
 template <class F2>
 B3_FN_NOINLINE void miller_dbl_step_u(miller_pt_t<F2>& t, F2& u0, F2& l3, F2& u5) {
-    F2 a, b, c, e, f, g, h, j, e2, u;
-    fp2_mul(a, t.x, t.y);
-    fp2_half(a, a);                 // A = XY/2
-    fp2_sqr(b, t.y);                // B = Y^2
-    fp2_sqr(c, t.z);                // C = Z^2
+    F2 a, b, c, e, f, g, h, j, e2, u, g2, x3, z3;
+    f_sqr_par(b, t.y, c, t.z);      // B = Y^2, C = Z^2
+    fp2_add(h, t.y, t.z);
+    f_sqr_par(h, h, j, t.x);        // (Y + Z)^2, J = X^2
     fp2_mul3(u, c);
     f_mul_b(e, u);                  // E = 3 b' C
     fp2_mul3(f, e);                 // F = 3E
     fp2_add(g, b, f);
     fp2_half(g, g);                 // G = (B+F)/2
-    fp2_add(h, t.y, t.z);
-    fp2_sqr(h, h);
     fp2_add(u, b, c);
     fp2_sub(h, h, u);               // H = 2YZ
-    fp2_sqr(j, t.x);                // J = X^2
-    fp2_sqr(e2, e);
+    f_sqr_par(e2, e, g2, g);        // E^2, G^2
+    f_mul_par(a, t.x, t.y, z3, b, h);   // XY, Z3 = B H
+    fp2_half(a, a);                 // A = XY/2
     fp2_sub(l3, e, b);
     fp2_mul3(u5, j);
     fp2_mul_xi(u0, h);
     fp2_sub(u, b, f);
-    fp2_mul(t.x, a, u);             // X3 = A (B - F)
-    fp2_sqr(g, g);
+    f_mul(x3, a, u);                // X3 = A (B - F)
+    t.x = x3;
     fp2_mul3(u, e2);
-    fp2_sub(t.y, g, u);             // Y3 = G^2 - 3 E^2
-    fp2_mul(t.z, b, h);             // Z3 = B H
+    fp2_sub(t.y, g2, u);            // Y3 = G^2 - 3 E^2
+    t.z = z3;
 }
 // Unscaled addition step T <- T + Q with Q = (X2 : Y2 : Z2) homogeneous projective (x2 = X2/Z2, y2 = Y2/Z2), so that
 // hash_to_curve outputs never have to be normalised.  It is the mixed step (A/pair.rs:88-133) with theta, lambda and
@@ -135,36 +133,29 @@ B3_FN_NOINLINE void miller_dbl_step_u(miller_pt_t<F2>& t, F2& u0, F2& l3, F2& u5
 //   theta = Y1 Z2 - Y2 Z1,  lambda = X1 Z2 - X2 Z1.
 template <class F2>
 B3_FN_NOINLINE void miller_add_step_u(miller_pt_t<F2>& t, F2& u0, F2& l3, F2& u5, const F2& xq, const F2& yq, const F2& zq) {
-    F2 theta, lambda, c, d, e, f, g, h, u, xz, yz, zz;
-    fp2_mul(xz, t.x, zq);
-    fp2_mul(yz, t.y, zq);
-    fp2_mul(zz, t.z, zq);
-    fp2_mul(u, yq, t.z);
+    F2 theta, lambda, c, d, e, f, g, h, u, v, xz, yz, zz, x3, z3;
+    f_mul_par(xz, t.x, zq, yz, t.y, zq);
+    f_mul_par(zz, t.z, zq, u, yq, t.z);
     fp2_sub(theta, yz, u);
-    fp2_mul(u, xq, t.z);
-    fp2_sub(lambda, xz, u);
-    fp2_sqr(c, theta);
-    fp2_sqr(d, lambda);
-    fp2_mul(e, lambda, d);
-    fp2_mul(f, zz, c);
-    fp2_mul(g, xz, d);
+    f_mulsqr_par(v, xq, t.z, c, theta);
+    fp2_sub(lambda, xz, v);
+    f_mulsqr_par(f, zz, c, d, lambda);
+    f_mul_par(e, lambda, d, g, xz, d);
     fp2_add(h, e, f);
     fp2_sub(h, h, g);
     fp2_sub(h, h, g);               // H = E + F - 2G
-    fp2_mul(l3, theta, xq);
-    fp2_mul(u, lambda, yq);
+    f_mul_par(l3, theta, xq, u, lambda, yq);
     fp2_sub(l3, l3, u);
-    fp2_mul(u, theta, zq);
+    f_mul_par(u, theta, zq, v, lambda, zq);
     fp2_neg(u5, u);
-    fp2_mul(u, lambda, zq);
-    fp2_mul_xi(u, u);
-    fp2_neg(u0, u);
-    fp2_mul(t.x, lambda, h);
+    fp2_mul_xi(v, v);
+    fp2_neg(u0, v);
     fp2_sub(u, g, h);
-    fp2_mul(u, theta, u);
-    fp2_mul(g, e, yz);
-    fp2_sub(t.y, u, g);
-    fp2_mul(t.z, zz, e);
+    f_mul_par(x3, lambda, h, v, theta, u);
+    f_mul_par(g, e, yz, z3, zz, e);
+    t.x = x3;
+    fp2_sub(t.y, v, g);
+    t.z = z3;
 }
 // Start of a point chain from a Jacobian Q = (X : Y : Z), x = X/Z^2, y = Y/Z^3: homogeneous (X Z : Y : Z^3)
 template <class F2>

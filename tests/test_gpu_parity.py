@@ -512,6 +512,39 @@ def test_verify_multiple_large_batch_edge_sets(eng):
     assert not ok and fb == 377
 
 
+@pytest.mark.parametrize("mode", [1, 2], ids=["replicated_lanes", "plain"])
+def test_verify_multiple_latency_modes_vs_c_oracle(eng, mode):
+    """Both forms of the chain kernels (quad.cuh: lane pairs / quads with the paired products of every point formula split
+    over their halves, and the plain one-thread / lane-pair form) against the C oracle: 530 sets x 3 keys, a rejecting batch
+    (GT != 1 must match byte for byte), a set with an infinite signature and key, and a non-subgroup signature (first_bad)."""
+    from oracle import c_oracle
+    rnd = random.Random(40 + mode)
+    n, nk = 530, 3
+    sks = [rnd.randrange(1, O.r) for _ in range(n * nk)]
+    pk = eng.g1_mul_gen(sks).copy()
+    msgs = [bytes(rnd.getrandbits(8) for _ in range(32)) for _ in range(n)]
+    H = eng.hash_to_g2(msgs)
+    sig = eng.g2_mul(H.reshape(-1), [sum(sks[j * nk:(j + 1) * nk]) % O.r for j in range(n)]).copy()
+    scalars = np.array([rnd.randrange(1, 1 << 63) for _ in range(n)], dtype=np.uint64)
+    scalars[0] = 1
+    scalars[1] = (1 << 63) - 1
+    offs = list(range(0, n * nk + 1, nk))
+    moff = list(range(0, 32 * n + 1, 32))
+    eng.set_latency_mode(mode)
+    try:
+        ok, fb, gt = eng.verify_multiple(sig.reshape(-1), pk.reshape(-1), offs, b"".join(msgs), moff, scalars, want_gt=True)
+        assert ok and fb == -1 and gt == O.f12_to_bytes(O.F12_ONE)
+        sw = sig.copy(); sw[[5, 6]] = sw[[6, 5]]
+        ok, fb, gt = eng.verify_multiple(sw.reshape(-1), pk.reshape(-1), offs, b"".join(msgs), moff, scalars, want_gt=True)
+        ok_c, gt_c = c_oracle.verify_multiple(sw.reshape(-1), pk.reshape(-1), offs, b"".join(msgs), moff, scalars)
+        assert not ok and not ok_c and fb == -1 and gt == gt_c and gt != O.f12_to_bytes(O.F12_ONE)
+        bad = sig.copy(); bad[377] = np.frombuffer(g2w(O.map_to_curve_g2((5, 7))), dtype=np.uint8)
+        ok, fb = eng.verify_multiple(bad.reshape(-1), pk.reshape(-1), offs, b"".join(msgs), moff, scalars)
+        assert not ok and fb == 377
+    finally:
+        eng.set_latency_mode(0)
+
+
 # ---------------------------------------------------------------- batched per-item verification (b3_verify_batch)
 def _batch_items():
     """A mixed bag of items: (sig point, [key points], msg).  Valid, wrong message, wrong key, non-subgroup signature,
