@@ -320,16 +320,7 @@ B3_FN void g1_phi(g1_jac& r, const g1_jac& p) { fp_mul(r.x, p.x, FP_BETA); r.y =
 // Subgroup membership.  The reference tests [r]P == O through its GLV/GS ladders
 // (A/bls381/core.rs:116-127 -> A/pair.rs:625-693); any exact membership test gives the same answer on
 // every on-curve input.  G2: psi(P) == [x]P = -[|x|]P.  G1: phi(P) == [-x^2]P.
-template <class F2>
-B3_FN_NOINLINE bool g2_in_subgroup(const jac<F2>& p) {
-    if (pt_is_inf(p)) return true;
-    jac<F2> xp, ps;
-    pt_mul_u64(xp, p, B3_X_ABS);
-    pt_neg(xp, xp);
-    g2_psi(ps, p);
-    return pt_eq(xp, ps);
-}
-// the same for an affine point: the five additions of the [|x|] ladder are mixed (7M + 4S instead of 11M + 5S)
+// (signatures are parsed to affine form: the five additions of the [|x|] ladder are mixed, 7M + 4S instead of 11M + 5S)
 template <class F2>
 B3_FN_NOINLINE bool g2_in_subgroup_aff(const aff<F2>& a) {
     if (a.inf) return true;

@@ -149,7 +149,7 @@ B3_FN_NOINLINE void hash_to_field_fp2_x2(fp2& u0, fp2& u1, const uint8_t* msg, u
 //   tv1 = Z u^2, tv2 = tv1^2 + tv1, x1 = (-B/A)(1 + 1/tv2) = -B (tv2 + 1) / (A tv2)   (tv2 == 0: x1 = B/(Z A))
 //   gx1 = (xn^3 + A xn xd^2 + B xd^3) / xd^3;  y1 = sqrt(gx1) or, if gx1 is not a square,
 //   x2 = tv1 x1 and y2 = tv1 u sqrt(Z gx1)     (RFC 9380 F.2 straight-line version)
-B3_FN_NOINLINE void sswu_g2(fp2& xn, fp2& xd, fp2& y, const fp2& u, fp2* dbg = nullptr) {
+B3_FN_NOINLINE void sswu_g2(fp2& xn, fp2& xd, fp2& y, const fp2& u) {
     fp2 tv1, tv2, gxn, gxd, t, t2;
     fp2_sqr(tv1, u);
     fp2_mul(tv1, tv1, SSWU_Z);
@@ -178,16 +178,12 @@ B3_FN_NOINLINE void sswu_g2(fp2& xn, fp2& xd, fp2& y, const fp2& u, fp2* dbg = n
     // y1 = sqrt(gxn / gxd) or, if that is not a square, sqrt(Z gxn / gxd): two Fp exponentiations, no inversion
     fp2 root;
     bool sq = fp2_sqrt_ratio_or_z(root, gxn, gxd);
-    if (dbg) { dbg[0] = root; dbg[1] = root; }
     if (!sq) {
         fp2_mul(xn, xn, tv1);                   // x2 = tv1 x1
         fp2_mul(t, tv1, u);
-        if (dbg) dbg[2] = t;
         fp2_mul(root, root, t);                 // y2 = tv1 u sqrt(Z gx1)
     }
-    if (dbg) dbg[3] = root;
     if (fp2_sgn0(u) != fp2_sgn0(root)) fp2_neg(root, root);
-    if (dbg) dbg[4] = root;
     y = root;
 }
 
@@ -244,15 +240,4 @@ B3_FN_NOINLINE void map_to_curve_g2(g2_jac& r, const fp2& u) {
     fp2 xn, xd, y;
     sswu_g2(xn, xd, y, u);
     iso3_g2(r, xn, xd, y);
-}
-
-// full hash_to_curve_g2, Jacobian output (not normalised)
-B3_FN_NOINLINE void hash_to_g2_jac(g2_jac& r, const uint8_t* msg, uint32_t msg_len, const uint8_t* dst, uint32_t dst_len) {
-    fp2 u0, u1;
-    hash_to_field_fp2_x2(u0, u1, msg, msg_len, dst, dst_len);
-    g2_jac q0, q1;
-    map_to_curve_g2(q0, u0);
-    map_to_curve_g2(q1, u1);
-    pt_add(q0, q0, q1);
-    g2_clear_cofactor(r, q0);
 }

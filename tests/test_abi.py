@@ -36,6 +36,24 @@ def test_python_binding_covers_header(built):
     _lib.lib()
 
 
+def test_rust_shim_binds_exactly_the_header():
+    """shim/src/b200/ffi.rs (the reference-side binding a maintainer adds; not compiled here: no rustc) declares exactly the
+    functions of the header, each with the header's number of parameters."""
+    rs = open(os.path.join(ROOT, "shim", "src", "b200", "ffi.rs")).read()
+    rs_fns = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (b3_[a-z0-9_]+)\(([^)]*)\)", rs, flags=re.S)}
+    assert sorted(rs_fns) == _declared_symbols()
+    txt = open(os.path.join(ROOT, "include", "milagro_bls_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    for name, args in re.findall(r"\b(b3_[a-z0-9_]+)\s*\(([^)]*)\)", txt, flags=re.S):
+        n_c = 0 if args.strip() in ("", "void") else args.count(",") + 1
+        n_rs = 0 if not rs_fns[name].strip() else rs_fns[name].count(",") + 1
+        assert n_c == n_rs, f"{name}: {n_c} parameters in the header, {n_rs} in ffi.rs"
+    # the method bodies only call functions that ffi.rs declares
+    for f in ("keys_b200.rs", "signature_b200.rs", "aggregates_b200.rs", os.path.join("b200", "ctx.rs")):
+        for used in set(re.findall(r"\b(b3_[a-z0-9_]+)\s*\(", open(os.path.join(ROOT, "shim", "src", f)).read())):
+            assert used in rs_fns, f"{f} calls undeclared {used}"
+
+
 def test_no_cpu_fallback(built):
     import torch
     if torch.cuda.is_available():

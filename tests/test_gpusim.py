@@ -3,6 +3,7 @@
 (PTX carry chains, stack, constant memory) to a single primitive."""
 import ctypes
 import os
+import sys
 import subprocess
 
 import pytest
@@ -17,7 +18,12 @@ SRC = os.path.join(HERE, "hostsim", "gpusim.cu")
 
 @pytest.fixture(scope="module")
 def hs():
-    if not os.path.exists(LIB):
+    csrc = os.path.join(HERE, "..", "milagro_bls_b200", "csrc")
+    gen = os.path.join(HERE, "hostsim", "make_gpusim.py")
+    deps = [os.path.join(HERE, "hostsim", f) for f in ("hostsim.cpp", "test_only.cuh", "make_gpusim.py")]
+    deps += [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+        subprocess.check_call([sys.executable, gen])          # regenerate gpusim.cu from hostsim.cpp
         subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
                                "-shared", "-o", LIB, SRC])
     lib = ctypes.CDLL(LIB)

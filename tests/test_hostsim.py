@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "..", "milagro_bls_b200", "csrc")
 
 @pytest.fixture(scope="module")
 def hs():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    deps = [SRC, os.path.join(HERE, "hostsim", "test_only.cuh")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-x", "c++", "-shared", "-fPIC", "-o", LIB, SRC])
     lib = ctypes.CDLL(LIB)
