@@ -441,7 +441,7 @@ def _bench_lanes(eng, comm, table, lanes, setup, args, world, rank, local_rank, 
         on its own context and host thread), batch i on lane i % L.  src: "dev" = inputs resident in HBM (device-pointer entries),
         "pinned" / "pageable" = host buffers through the host-pointer entries (H2D + D2H inside the call).  keys: "table" = u32
         indices into the device-resident key table, "bytes" = 96-byte uncompressed keys.
-        N = 1: b3_verify_multiple[_indexed] (host) or b3_verify_multiple[_indexed]_partial_dev + b3_combine_partials_dev.
+        N = 1: b3_verify_multiple[_indexed] (host pointers) or b3_verify_multiple[_indexed]_dev (device pointers).
         N > 1: b3_sharded_begin / b3_sharded_finish -- the all-gather of a step's partials is issued inside the library; a lane
         begins call k + 1 before it finishes call k, so the collective has a whole call time to complete."""
         L = len(use_lanes)
@@ -489,9 +489,8 @@ def _bench_lanes(eng, comm, table, lanes, setup, args, world, rank, local_rank, 
                                 results[i] = e.verify_multiple(h["sigs"], h["pks"], h["pk_off"], h["msgs"], h["msg_off"], h["scal"], want_gt=True)
                             add_stages(e)
                             continue
-                        ln.partial_dev(n, base, partials[i].data_ptr(), keys)
-                        add_stages(e)
-                        results[i] = e.combine_partials_dev(partials[i].data_ptr(), 1, want_gt=want_gt)
+                        results[i] = e.verify_multiple_dev(tbl, d["sigs"].data_ptr(), d[kname].data_ptr(), d["pk_off"].data_ptr(), d["msgs"].data_ptr(),
+                                                           d["msg_off"].data_ptr(), d["scal"].data_ptr(), n, want_gt=True)
                         add_stages(e)
                     if pending is not None:
                         results[pending[0]] = e.sharded_finish(comm, ln.index, pending[1], want_gt=want_gt)

@@ -157,6 +157,15 @@ int b3_verify_multiple_indexed(b3_ctx*, const b3_keytable*, const uint8_t* sigs1
                                const uint32_t* pk_off, const uint8_t* msgs, const uint32_t* msg_off,
                                const uint64_t* scalars, size_t n, int* accept, int64_t* first_bad, uint8_t* gt576);
 
+/* b3_verify_multiple / b3_verify_multiple_indexed on inputs already resident in HBM: every input pointer is DEVICE memory
+ * (signature and key records 16-byte aligned); accept, first_bad and gt576 are host pointers. */
+int b3_verify_multiple_dev(b3_ctx*, const uint8_t* sigs192_dev, const uint8_t* pks96_dev, const uint32_t* pk_off_dev,
+                           const uint8_t* msgs_dev, const uint32_t* msg_off_dev, const uint64_t* scalars_dev, size_t n,
+                           int* accept, int64_t* first_bad, uint8_t* gt576);
+int b3_verify_multiple_indexed_dev(b3_ctx*, const b3_keytable*, const uint8_t* sigs192_dev, const uint32_t* key_idx_dev,
+                                   const uint32_t* pk_off_dev, const uint8_t* msgs_dev, const uint32_t* msg_off_dev,
+                                   const uint64_t* scalars_dev, size_t n, int* accept, int64_t* first_bad, uint8_t* gt576);
+
 /* ---- batched verification of n INDEPENDENT items with one accept bit each (locating the bad set
  *      after a batch reject, or bulk verification of unrelated signatures).  Item i is, by `mode`,
  *        B3_ITEM_VERIFY          Signature::verify(sig_i, msg_i, pk_i)                           (M/src/signature.rs:27-40)

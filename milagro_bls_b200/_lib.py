@@ -65,6 +65,8 @@ def lib():
         "b3_fast_aggregate_verify_pre_aggregated": ([vp, u8p, u8p, u8p, sz, ip, u8p], ctypes.c_int),
         "b3_aggregate_verify": ([vp, u8p, u8p, u8p, vp, sz, ip, u8p], ctypes.c_int),
         "b3_verify_multiple": ([vp, u8p, u8p, vp, u8p, vp, vp, sz, ip, i64p, u8p], ctypes.c_int),
+        "b3_verify_multiple_dev": ([vp, vp, vp, vp, vp, vp, vp, sz, ip, i64p, u8p], ctypes.c_int),
+        "b3_verify_multiple_indexed_dev": ([vp, vp, vp, vp, vp, vp, vp, vp, sz, ip, i64p, u8p], ctypes.c_int),
         "b3_sig_precheck": ([vp, u8p, sz, i64p], ctypes.c_int),
         "b3_verify_multiple_checked": ([vp, u8p, vp, u8p, vp, vp, sz, ip, u8p], ctypes.c_int),
         "b3_keytable_create": ([vp, sz, ctypes.POINTER(vp)], ctypes.c_int),

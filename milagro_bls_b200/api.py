@@ -299,6 +299,20 @@ class Engine:
                                            ctypes.byref(ok), ctypes.byref(fb), gt.ctypes.data))
         return (bool(ok.value), int(fb.value), gt.tobytes()) if want_gt else (bool(ok.value), int(fb.value))
 
+    def verify_multiple_dev(self, table, d_sigs, d_keys, d_pk_off, d_msgs, d_msg_off, d_scalars, n, want_gt=False):
+        """The whole call on inputs resident in HBM (device pointers as integers).  table None: d_keys = 96-byte records
+        (b3_verify_multiple_dev); else u32 indices into the table (b3_verify_multiple_indexed_dev).  Returns (accept, first_bad[, gt])."""
+        ok = ctypes.c_int(0)
+        fb = ctypes.c_int64(-1)
+        gt = np.zeros(576, dtype=np.uint8)
+        if table is None:
+            self._ck(self.L.b3_verify_multiple_dev(self.handle, d_sigs, d_keys, d_pk_off, d_msgs, d_msg_off, d_scalars, n,
+                                                   ctypes.byref(ok), ctypes.byref(fb), gt.ctypes.data))
+        else:
+            self._ck(self.L.b3_verify_multiple_indexed_dev(self.handle, table.handle, d_sigs, d_keys, d_pk_off, d_msgs, d_msg_off, d_scalars, n,
+                                                           ctypes.byref(ok), ctypes.byref(fb), gt.ctypes.data))
+        return (bool(ok.value), int(fb.value), gt.tobytes()) if want_gt else (bool(ok.value), int(fb.value))
+
     def sig_precheck(self, sigs192):
         """Phase one of the two-phase call: upload, parse and subgroup-check the signatures; returns first_bad (-1: all passed).
         The checked signatures stay in this context for verify_multiple_checked / verify_multiple_indexed(sigs192=None)."""

@@ -51,7 +51,8 @@ struct b3_ctx {
     float stage_ms[B3_N_STAGES];
     // independent stages of verify_multiple run concurrently on aux streams (fork/join by events) unless serial != 0
     cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_fork2 = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_fork2 = nullptr, ev_fork3 = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool sig_pending = false;       // the subgroup checks of the call run on aux[0] beside the closing chain: join before reading first_bad
     int serial = 0;
     int latency_mode = 0;           // chain kernels: 0 = replicated lanes (quad.cuh) when this is the only call in flight on the device, 1 = always, 2 = never
     bool wide_now = false;          // decision for the call being enqueued
@@ -132,6 +133,7 @@ extern "C" int b3_ctx_create(int device, b3_ctx** out) {
              cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork3, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < B3_N_STAGES; i++) ctx->stage_ms[i] = 0.f;
     ok = ok && cudaMalloc((void**)&ctx->d_dst, 256) == cudaSuccess;
     ok = ok && cudaMemcpy(ctx->d_dst, kDstG2, kDstG2Len, cudaMemcpyHostToDevice) == cudaSuccess;
@@ -165,6 +167,7 @@ extern "C" void b3_ctx_destroy(b3_ctx* ctx) {
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_fork2) cudaEventDestroy(ctx->ev_fork2);
+    if (ctx->ev_fork3) cudaEventDestroy(ctx->ev_fork3);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     cudaGetLastError();
     delete ctx;
@@ -302,7 +305,8 @@ static int miller_finish_reserve(b3_ctx* ctx, size_t n_pairs) {
     miller_shape(n_pairs, &chunks, &K);
     return ensure(ctx, ctx->f12a, sizeof(fp12) * (B3_MILLER_SLOTS * (chunks + 1) + 2));
 }
-static int miller_finish(b3_ctx* ctx, const g1_pp* p, size_t n_pairs, fp12** res) {
+// step 2: the accumulation kernel (wide: fills the GPU); step 3 (miller_close): slot products and the closing chain (one CTA)
+static int miller_accumulate(b3_ctx* ctx, const g1_pp* p, size_t n_pairs, fp12** res) {
     size_t chunks;
     unsigned K;
     miller_shape(n_pairs, &chunks, &K);
@@ -311,16 +315,26 @@ static int miller_finish(b3_ctx* ctx, const g1_pp* p, size_t n_pairs, fp12** res
     fp12* slotvals = partial + B3_MILLER_SLOTS * chunks;
     fp12* out = slotvals + B3_MILLER_SLOTS;
     *res = out;
-    if (n_pairs == 0) {
-        LAUNCH(k_fp12_set_one, 1, 1, out);
-        return B3_OK;
-    }
+    if (n_pairs == 0) return B3_OK;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     int sp = span_begin(ctx, ST_MILLER, ctx->stream);
     LAUNCH(k_miller_accum, dim3((unsigned)chunks, B3_MILLER_SLOTS), B3_TPB, (const fp2*)ctx->lines.p, (const uint32_t*)ctx->qinf.p, p, n_pairs, K, partial);
     span_end(ctx, sp, ctx->stream);
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-    sp = span_begin(ctx, ST_FP12_PRODUCT, ctx->stream);
+    return B3_OK;
+}
+static int miller_close(b3_ctx* ctx, size_t n_pairs) {
+    size_t chunks;
+    unsigned K;
+    miller_shape(n_pairs, &chunks, &K);
+    fp12* partial = (fp12*)ctx->f12a.p;
+    fp12* slotvals = partial + B3_MILLER_SLOTS * chunks;
+    fp12* out = slotvals + B3_MILLER_SLOTS;
+    if (n_pairs == 0) {
+        LAUNCH(k_fp12_set_one, 1, 1, out);
+        return B3_OK;
+    }
+    int sp = span_begin(ctx, ST_FP12_PRODUCT, ctx->stream);
     if (chunks > 1) {
         LAUNCH(k_miller_slots, B3_MILLER_SLOTS, B3_COOP_THREADS, (const fp12*)partial, (unsigned)chunks, slotvals);
         LAUNCH(k_miller_chain, 1, B3_COOP_THREADS, (const fp12*)slotvals, 1u, out);
@@ -329,6 +343,10 @@ static int miller_finish(b3_ctx* ctx, const g1_pp* p, size_t n_pairs, fp12** res
     }
     span_end(ctx, sp, ctx->stream);
     return B3_OK;
+}
+static int miller_finish(b3_ctx* ctx, const g1_pp* p, size_t n_pairs, fp12** res) {
+    CKR(miller_accumulate(ctx, p, n_pairs, res));
+    return miller_close(ctx, n_pairs);
 }
 // whole product on the context stream
 static int miller_product(b3_ctx* ctx, const g2_jac* q, const g1_pp* p, size_t n_pairs, fp12** res) {
@@ -950,6 +968,7 @@ struct vm_in {
     size_t n = 0;
     long long index_base = 0;
     bool prechecked = false;                // parsed signatures and ok[] are already in the context (b3_sig_precheck)
+    bool defer_sig = false;                 // run the subgroup checks beside the serial tail of the call instead of at its start (whole calls)
 };
 #define B3_FB_NONE 0x7fffffffffffffffLL
 // one table entry per set (pre-aggregated keys held in the table)
@@ -975,6 +994,7 @@ __global__ void __launch_bounds__(B3_TPB) k_g1_from_table(const key_entry* __res
 //   aux0 : subgroup checks of the parsed signatures               aux1 : aggregate keys -> P_j = [c_j] apk_j
 //   aux2 : H_j = hash_to_curve_g2(msg_j) -> their point chains    aux3 : S = sum_j [c_j] sig_j -> its point chains
 // No allocation happens in here (every buffer is sized by the caller before the fork).
+static int vm_sig_checks(b3_ctx* ctx, const vm_in& in, const int32_t* d_st_sig, long long* d_first_bad);
 static int vm_stages(b3_ctx* ctx, const vm_in& in, size_t n_total, int32_t* d_st_sig, int32_t* d_st_key, long long* d_first_bad, int32_t* d_zero) {
     const size_t n = in.n;
     g2_jac* q = (g2_jac*)ctx->g2q.p;
@@ -1003,16 +1023,12 @@ static int vm_stages(b3_ctx* ctx, const vm_in& in, size_t n_total, int32_t* d_st
     }
     if (!ctx->serial) {
         CK(cudaEventRecord(ctx->ev_fork2, sm));
-        CK(cudaStreamWaitEvent(s0, ctx->ev_fork2, 0));
         CK(cudaStreamWaitEvent(s3, ctx->ev_fork2, 0));
     }
-    sp = span_begin(ctx, ST_SIG_CHECK, s0);
-    if (!in.prechecked) {
-        if (ctx->wide_now) LAUNCH_ON(s0, k_g2_subgroup_q, nblk(4 * n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, (const int32_t*)d_st_sig, n, (int32_t*)ctx->ok.p);
-        else LAUNCH_ON(s0, k_g2_subgroup, nblk(2 * n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, (const int32_t*)d_st_sig, n, (int32_t*)ctx->ok.p);
-    }
-    LAUNCH_ON(s0, k_first_bad, nblk(n), B3_TPB, (const int32_t*)ctx->ok.p, n, in.index_base, d_first_bad);
-    span_end(ctx, sp, s0);
+    // subgroup checks: a WHOLE call (in.defer_sig) runs them beside its closing chain and final exponentiation, when the GPU is
+    // otherwise idle (vm_enqueue) -- nothing before the accept bit needs their result; a PARTIAL call needs first_bad in its
+    // partial record right after the closing chain, so its checks start here, with the call
+    if (!in.defer_sig) CKR(vm_sig_checks(ctx, in, d_st_sig, d_first_bad));
     // 2. aggregate public keys; 3. P_j = [c_j] apk_j (M/src/aggregates.rs:293)
     // host-pointer entries: the keys (96 % of the input bytes) or their indices are copied on THIS stream, so the transfer
     // overlaps hash_to_G2 and the signature work instead of preceding them
@@ -1053,15 +1069,51 @@ static int vm_stages(b3_ctx* ctx, const vm_in& in, size_t n_total, int32_t* d_st
     CKR(miller_lines(ctx, s3, q, n_total, n, n_total - n));       // ... and the window sums / S
     if (!ctx->serial) {
         cudaStream_t auxs[4] = {s0, s1, s2, s3};
-        for (int k = 0; k < 4; k++) {
+        for (int k = 1; k < 4; k++) {
             CK(cudaEventRecord(ctx->ev_join[k], auxs[k]));
             CK(cudaStreamWaitEvent(sm, ctx->ev_join[k], 0));
         }
+        (void)s0;
+    }
+    return B3_OK;
+}
+// 1b. subgroup_check_g2 of every signature (M/src/aggregates.rs:274-276) and the index of the first failure.  Nothing before the
+//     accept bit needs the result, so the checks are forked off AFTER the accumulation kernel has been launched: they run on
+//     aux0 beside the closing chain and the final exponentiation -- single-CTA kernels that leave the GPU idle -- instead of
+//     competing with hash_to_G2 at the start of the call.  vm_join_sig() makes the context stream wait for them.
+static int vm_sig_checks(b3_ctx* ctx, const vm_in& in, const int32_t* d_st_sig, long long* d_first_bad) {
+    const size_t n = in.n;
+    cudaStream_t s0 = ctx->serial ? ctx->stream : ctx->aux[0];
+    if (!ctx->serial) {
+        CK(cudaEventRecord(ctx->ev_fork3, ctx->stream));
+        CK(cudaStreamWaitEvent(s0, ctx->ev_fork3, 0));
+    }
+    // beside the tail the plain kernel is used even in latency mode: at 8192 sets it has 128 CTAs, which leaves SMs free for
+    // the single CTA of the closing chain / final exponentiation (the replicated form fills every SM and halves their speed)
+    const bool wide = ctx->wide_now && !in.defer_sig;
+    int sp = span_begin(ctx, ST_SIG_CHECK, s0);
+    if (!in.prechecked) {
+        if (wide) LAUNCH_ON(s0, k_g2_subgroup_q, nblk(4 * n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, d_st_sig, n, (int32_t*)ctx->ok.p);
+        else LAUNCH_ON(s0, k_g2_subgroup, nblk(2 * n), B3_TPB, (const g2_aff*)ctx->g2a_sig.p, d_st_sig, n, (int32_t*)ctx->ok.p);
+    }
+    LAUNCH_ON(s0, k_first_bad, nblk(n), B3_TPB, (const int32_t*)ctx->ok.p, n, in.index_base, d_first_bad);
+    span_end(ctx, sp, s0);
+    if (!ctx->serial) {
+        CK(cudaEventRecord(ctx->ev_join[0], s0));
+        ctx->sig_pending = true;
+    }
+    return B3_OK;
+}
+static int vm_join_sig(b3_ctx* ctx) {
+    if (ctx->sig_pending) {
+        ctx->sig_pending = false;
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
     }
     return B3_OK;
 }
 // an error inside the forked region leaves aux streams running (possibly still reading the caller's host buffers): drain them
 static void vm_drain(b3_ctx* ctx) {
+    ctx->sig_pending = false;
     for (int i = 0; i < 4; i++) cudaStreamSynchronize(ctx->aux[i]);
     cudaStreamSynchronize(ctx->stream);
     cudaGetLastError();
@@ -1108,8 +1160,13 @@ static int vm_enqueue(b3_ctx* ctx, const vm_in& in, fp12** res, long long** d_fi
         const int rc = vm_stages(ctx, in, n_total, d_st_sig, d_st_key, d_first_bad, d_zero);
         if (rc != B3_OK) { vm_drain(ctx); return rc; }
     }
-    // 6. Miller loops over the n + 8 (or n + 1) pairs, product
-    CKR(miller_finish(ctx, (const g1_pp*)ctx->g1pp.p, n_total, res));
+    // 6. Miller loops over the n + 8 (or n + 1) pairs: accumulation, then -- beside the subgroup checks -- the closing chain
+    CKR(miller_accumulate(ctx, (const g1_pp*)ctx->g1pp.p, n_total, res));
+    if (n > 0 && in.defer_sig) {
+        const int rc = vm_sig_checks(ctx, in, d_st_sig, d_first_bad);
+        if (rc != B3_OK) { vm_drain(ctx); return rc; }
+    }
+    CKR(miller_close(ctx, n_total));
     *d_first_bad_out = d_first_bad;
     if (n > 0) CK(cudaMemcpyAsync(ctx->pin, ctx->status.p, 4 * (2 * n + 8), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync((uint8_t*)ctx->pin + 4 * (2 * n + 8), d_zero, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1140,6 +1197,7 @@ static int vm_finish_whole(b3_ctx* ctx, size_t n, fp12* res, long long* d_fb, in
     int sp = span_begin(ctx, ST_FINAL_EXP, ctx->stream);
     LAUNCH(k_final_exp, 1, B3_COOP_THREADS, (const fp12*)res, d_gt, d_one);
     span_end(ctx, sp, ctx->stream);
+    CKR(vm_join_sig(ctx));
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     int32_t one = 0;
     long long fb = 0;
@@ -1181,6 +1239,7 @@ __global__ void k_unpack_partials(const partial_rec* in, size_t n, size_t stride
 }
 // this rank's partial -> partial_dev, one synchronise
 static int vm_finish_partial(b3_ctx* ctx, size_t n, fp12* res, long long* d_fb, uint8_t* partial_dev) {
+    CKR(vm_join_sig(ctx));
     LAUNCH(k_pack_partial, 1, 1, (const fp12*)res, (const long long*)d_fb, (partial_rec*)partial_dev);
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     CKR(sync(ctx));
@@ -1246,8 +1305,10 @@ static int vm_begin(b3_ctx* ctx) {
     mark_reset(ctx);
     return B3_OK;
 }
-static int vm_whole(b3_ctx* ctx, const vm_in& in, int* accept, int64_t* first_bad, uint8_t* gt576) {
-    call_guard guard(ctx, in.n);
+static int vm_whole(b3_ctx* ctx, const vm_in& in0, int* accept, int64_t* first_bad, uint8_t* gt576) {
+    call_guard guard(ctx, in0.n);
+    vm_in in = in0;
+    in.defer_sig = true;                       // the final exponentiation follows in the same call: checks beside the serial tail
     fp12* res;
     long long* d_fb;
     CKR(vm_enqueue(ctx, in, &res, &d_fb));
@@ -1322,6 +1383,28 @@ extern "C" int b3_verify_multiple_indexed(b3_ctx* ctx, const b3_keytable* tbl, c
     return vm_whole(ctx, in, accept, first_bad, gt576);
 }
 
+// whole calls on inputs already resident in HBM (every pointer is device memory; results come back to the host)
+extern "C" int b3_verify_multiple_dev(b3_ctx* ctx, const uint8_t* sigs192_dev, const uint8_t* pks96_dev, const uint32_t* pk_off_dev,
+                                      const uint8_t* msgs_dev, const uint32_t* msg_off_dev, const uint64_t* scalars_dev, size_t n, int* accept,
+                                      int64_t* first_bad, uint8_t* gt576) {
+    if (accept) *accept = 0;
+    if (first_bad) *first_bad = -1;
+    CKR(vm_begin(ctx));
+    vm_in in;
+    CKR(vm_fill_dev(ctx, in, nullptr, sigs192_dev, pks96_dev, pk_off_dev, msgs_dev, msg_off_dev, scalars_dev, n, 0));
+    return vm_whole(ctx, in, accept, first_bad, gt576);
+}
+extern "C" int b3_verify_multiple_indexed_dev(b3_ctx* ctx, const b3_keytable* tbl, const uint8_t* sigs192_dev, const uint32_t* key_idx_dev,
+                                              const uint32_t* pk_off_dev, const uint8_t* msgs_dev, const uint32_t* msg_off_dev,
+                                              const uint64_t* scalars_dev, size_t n, int* accept, int64_t* first_bad, uint8_t* gt576) {
+    if (accept) *accept = 0;
+    if (first_bad) *first_bad = -1;
+    CKR(vm_begin(ctx));
+    if (!tbl) return B3_ERR_ARG;
+    vm_in in;
+    CKR(vm_fill_dev(ctx, in, tbl, sigs192_dev, key_idx_dev, pk_off_dev, msgs_dev, msg_off_dev, scalars_dev, n, 0));
+    return vm_whole(ctx, in, accept, first_bad, gt576);
+}
 extern "C" int b3_verify_multiple_partial_dev(b3_ctx* ctx, const uint8_t* sigs192_dev, const uint8_t* pks96_dev, const uint32_t* pk_off_dev,
                                               const uint8_t* msgs_dev, const uint32_t* msg_off_dev, const uint64_t* scalars_dev, size_t n,
                                               int64_t index_base, uint8_t* partial_dev) {

@@ -64,6 +64,12 @@ extern "C" {
                                accept: *mut c_int, gt576: *mut u8) -> c_int;
     pub fn b3_verify_multiple(ctx: *mut b3_ctx, sigs192: *const u8, pks96: *const u8, pk_off: *const u32, msgs: *const u8, msg_off: *const u32,
                               scalars: *const u64, n: usize, accept: *mut c_int, first_bad: *mut i64, gt576: *mut u8) -> c_int;
+    pub fn b3_verify_multiple_dev(ctx: *mut b3_ctx, sigs192_dev: *const u8, pks96_dev: *const u8, pk_off_dev: *const u32, msgs_dev: *const u8,
+                                  msg_off_dev: *const u32, scalars_dev: *const u64, n: usize, accept: *mut c_int, first_bad: *mut i64,
+                                  gt576: *mut u8) -> c_int;
+    pub fn b3_verify_multiple_indexed_dev(ctx: *mut b3_ctx, t: *const b3_keytable, sigs192_dev: *const u8, key_idx_dev: *const u32,
+                                          pk_off_dev: *const u32, msgs_dev: *const u8, msg_off_dev: *const u32, scalars_dev: *const u64,
+                                          n: usize, accept: *mut c_int, first_bad: *mut i64, gt576: *mut u8) -> c_int;
     // two-phase form: the RNG contract of M/aggregates.rs:272-287 without running the subgroup checks twice
     pub fn b3_sig_precheck(ctx: *mut b3_ctx, sigs192: *const u8, n: usize, first_bad: *mut i64) -> c_int;
     pub fn b3_verify_multiple_checked(ctx: *mut b3_ctx, pks96: *const u8, pk_off: *const u32, msgs: *const u8, msg_off: *const u32,

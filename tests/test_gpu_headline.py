@@ -129,6 +129,24 @@ def test_c4_key_table_and_two_phase_match_byte_entry(eng, c4):
         assert eng.sig_precheck(c4["sigs"]) == -1
         got = eng.verify_multiple_indexed(tbl, None, kidx, c4["pk_off"], msgs.reshape(-1), c4["moff"], c4["scalars"], want_gt=True)
         assert got == ref
+    # the whole call on inputs resident in HBM (b3_verify_multiple_dev / _indexed_dev), valid, tampered and with a non-subgroup signature
+    import torch
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+    sig_bad = c4["sigs"].copy()
+    sig_bad[192 * 4242:192 * 4243] = np.frombuffer(g2w(O.map_to_curve_g2((5, 7))), dtype=np.uint8)
+    d_pks, d_idx, d_koff = t(c4["pks"]), t(kidx.astype(np.uint32)), t(np.asarray(c4["pk_off"], dtype=np.uint32))
+    d_moff, d_sc = t(np.asarray(c4["moff"], dtype=np.uint32)), t(np.asarray(c4["scalars"], dtype=np.uint64))
+    for sigs, msgs in ((c4["sigs"], c4["msgs"]), (c4["sigs"], tam), (sig_bad, c4["msgs"])):
+        d_sigs, d_msgs = t(sigs), t(msgs)
+        torch.cuda.synchronize()
+        ref = eng.verify_multiple(sigs, c4["pks"], c4["pk_off"], msgs.reshape(-1), c4["moff"], c4["scalars"], want_gt=True)
+        a = eng.verify_multiple_dev(None, d_sigs.data_ptr(), d_pks.data_ptr(), d_koff.data_ptr(), d_msgs.data_ptr(), d_moff.data_ptr(),
+                                    d_sc.data_ptr(), len(c4["scalars"]), want_gt=True)
+        b = eng.verify_multiple_dev(tbl, d_sigs.data_ptr(), d_idx.data_ptr(), d_koff.data_ptr(), d_msgs.data_ptr(), d_moff.data_ptr(),
+                                    d_sc.data_ptr(), len(c4["scalars"]), want_gt=True)
+        assert a == ref and b == ref
+    assert ref[1] == 4242 and not ref[0]
     # a *_checked call without its precheck is refused
     with pytest.raises(RuntimeError):
         eng.verify_multiple_checked(c4["pks"], c4["pk_off"], c4["msgs"].reshape(-1), c4["moff"], c4["scalars"])
