@@ -4,9 +4,12 @@
  * built here: no rustc/cargo).  A = /root/reference/incubator-milagro-crypto-rust/src, M = /root/reference/src.
  *   - Fp: Montgomery residues with 128-bit accumulators (A/big.rs:950-1106, A/fp.rs:306-314).  Limbs here are
  *     6 x 64-bit (R = 2^384) instead of the reference's 7 x 58-bit with lazy-reduction excess counters: 36 + 42
- *     64-bit products per multiplication against the reference's 28 + 41 on 58-bit limbs.  As in the reference, the
- *     squaring is dedicated (cross products once, doubled: A/big.rs:991-1058), Fp powers use fixed 4-bit windows
- *     (A/fp.rs:635-686) and the Fp2 product is lazily reduced (three 768-bit products, two reductions: A/fp2.rs:258-300).
+ *     64-bit products per multiplication against the reference's 28 + 41 on 58-bit limbs.  As in the reference, Fp powers
+ *     use fixed 4-bit windows (A/fp.rs:635-686) and the Fp2 product is lazily reduced (three 768-bit products, two
+ *     reductions: A/fp2.rs:258-300; -DORACLE_FP2_LAZY).  The reference's dedicated squaring (cross products once, doubled:
+ *     A/big.rs:991-1058) is available as -DORACLE_SQR_DEDICATED but measured SLOWER than the CIOS product on the GPU box's
+ *     host CPU, so the baseline build leaves it off: the Makefile picks the fastest measured combination
+ *     (oracle/tools/compare_field_variants.sh) -- a baseline must not be slowed down in the name of fidelity.
  *   - Fp2 / Fp4 / Fp12 tower of A/fp2.rs, A/fp4.rs, A/fp12.rs (2-2-3), sparse line products.
  *   - complete projective point formulas (A/ecp.rs:552-592,743-819, A/ecp2.rs:368-527): oracle/ec_generic.inc.
  *   - GLV / GS scalar paths with full-length joint ladders, incl. the [r]P subgroup checks
@@ -109,7 +112,11 @@ static void wide_redc(fp_t *r, const wide_t *T) {
     }
     if (t[12] || raw_geq(t + 6, FP_P.l)) raw_sub(r->l, t + 6, FP_P.l); else memcpy(r->l, t + 6, 48);
 }
+#if defined(ORACLE_SQR_DEDICATED)
 static void fp_sqr(fp_t *r, const fp_t *a) { wide_t w; wide_sqr(&w, a->l); wide_redc(r, &w); }      /* A/fp.rs:390-398 */
+#else
+static void fp_sqr(fp_t *r, const fp_t *a) { fp_mul(r, a, a); }
+#endif
 /* A/fp.rs:635-686: fixed 4-bit windows over a table of a^0 .. a^15, four squarings and ONE multiplication per window
  * (also for a zero window, as the reference does) */
 static void fp_pow(fp_t *r, const fp_t *a, const fp_t *e) {
@@ -189,6 +196,7 @@ static void wide_sub(wide_t *r, const wide_t *a, const wide_t *b) {
     u128 br = 0;
     for (int i = 0; i < 12; i++) { u128 t = (u128)a->l[i] - b->l[i] - br; r->l[i] = (uint64_t)t; br = (t >> 64) & 1; }
 }
+#if defined(ORACLE_FP2_LAZY)
 static void f2_mul(fp2_t *r, const fp2_t *x, const fp2_t *y) {
     static wide_t PP; static int have_pp = 0;
     if (!have_pp) { wide_mul(&PP, FP_P.l, FP_P.l); have_pp = 1; }                /* p^2: keeps x.a y.a - x.b y.b non-negative */
@@ -202,6 +210,14 @@ static void f2_mul(fp2_t *r, const fp2_t *x, const fp2_t *y) {
     wide_redc(&ra, &t0); wide_redc(&rb, &t2);
     r->a = ra; r->b = rb;
 }
+#else
+static void f2_mul(fp2_t *r, const fp2_t *x, const fp2_t *y) {                  /* A/fp2.rs:258-300, every product reduced */
+    fp_t t0, t1, s0, s1;
+    fp_add(&s0, &x->a, &x->b); fp_add(&s1, &y->a, &y->b);
+    fp_mul(&t0, &x->a, &y->a); fp_mul(&t1, &x->b, &y->b); fp_mul(&s0, &s0, &s1);
+    fp_sub(&s0, &s0, &t0); fp_sub(&r->b, &s0, &t1); fp_sub(&r->a, &t0, &t1);
+}
+#endif
 static void f2_sqr(fp2_t *r, const fp2_t *x) {                                    /* A/fp2.rs:237-255 */
     fp_t s, d, m;
     fp_add(&s, &x->a, &x->b); fp_sub(&d, &x->a, &x->b); fp_mul(&m, &x->a, &x->b);

@@ -3,7 +3,7 @@
 The reference is single-threaded: "all host cores" means T independent single-threaded
 instances of verify_multiple_aggregate_signatures on disjoint chunks of the same workload, throughputs summed.
 kind = "port": the Rust crate cannot be compiled in this image (no rustc/cargo), so this is the oracle port, built
-with gcc -O3 -march=native.  TEST / MEASUREMENT INFRASTRUCTURE ONLY -- never on the product path.
+with gcc -O3 and the field-layer variant measured fastest on the GPU box's host CPU (oracle/Makefile).  TEST / MEASUREMENT INFRASTRUCTURE ONLY -- never on the product path.
 """
 import ctypes
 import os
