@@ -242,6 +242,7 @@ static int dev_aligned(b3_ctx* ctx, const void* p) {
 static int begin(b3_ctx* ctx) {
     if (!ctx) return B3_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
+    ctx->wide_now = false;                    // set per call by the call_guard of the verify_multiple entries
     return B3_OK;
 }
 
