@@ -58,8 +58,9 @@ FP_MULS_PER_SET = 16400
 # what this implementation actually executes per set (inversion-free maps, bucket-method sum, split
 # Miller loop), in the same unit -- reported beside the SURVEY figure so the fraction cannot flatter the kernels
 EXEC_FP_MULS_PER_SET = 12900
-# DRAM bytes (read + write) per launch at the C4 shape from the committed `ncu --set full` captures (profiles/r1s_h2c_full.txt, r1t_accum_full.txt)
-NCU_TRAFFIC_BYTES = {"hash_to_g2_affine": 534016 + 6311424, "miller_accumulate": 162358272 + 5568000}
+# DRAM bytes (read + write) per launch at the C4 shape from the committed `ncu --set full` capture profiles/r2p_c4_full.txt
+# (hash_to_G2: 0.26 MB of messages in, 2.36 MB of points out; the rest is write-back of its local-memory stack)
+NCU_TRAFFIC_BYTES = {"hash_to_g2_affine": 532480 + 6281728, "miller_accumulate": 162431232 + 5712384, "g1_aggregate": 10587392 + 11520}
 # 32x32->64 multiply-accumulates actually EXECUTED per unit (set / message / pair): IMAD.WIDE warp instructions x 32 lanes of the
 # `ncu --set full --import-source on` capture of a 32768-set call, divided by its units (profiles/r2c_big32768_opcodes.txt).
 # g1_aggregate is the byte-key kernel (parse + 2 Montgomery conversions + on-curve check per key on top of the 11-M mixed addition).
