@@ -53,7 +53,8 @@ R_ORDER = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
 # algorithmic work per unit: 32x32->64 multiply-accumulates, 300 per Fp multiplication
 MACS_PER_FP_MUL = 300
 FP_MULS = {"g1_aggregate": 1400, "g2_parse_subgroup_check": 1170, "hash_to_g2_affine": 6700, "g1_scalar_mul_affine": 670 + 15,
-           "g2_scalar_mul_sum": 1650, "miller_lines": 1800, "miller_accumulate": 3000, "miller_chain": 0, "final_exp": 0}
+           "g2_scalar_mul_sum": 1650, "miller_lines": 1800, "miller_accumulate": 3000, "miller_chain": 0, "final_exp": 0,
+           "miller_lines_signature_sums": 0}
 FP_MULS_PER_SET = 16400
 # what this implementation actually executes per set (inversion-free maps, bucket-method sum, split
 # Miller loop), in the same unit -- reported beside the SURVEY figure so the fraction cannot flatter the kernels
@@ -124,47 +125,74 @@ def draw_scalars(n, seed):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """Samples the SM clock and the throttle reasons of one GPU during the timed region (B200_PROFILING.md recipe).  NVML is
+    read in-process (nvidia_ml_py) every 20 ms: a polling `nvidia-smi -lms 100` process costs the GPU it watches ~3 % at
+    N = 8 (every rank waits for the slowest at the all-gather); the CLI is the fallback when the module is missing."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.mx, self.reasons, self.proc, self.stop_ev, self.t = index, [], [], set(), None, threading.Event(), None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t = threading.Thread(target=self._read_cli, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+    def _poll_nvml(self):
+        nv = self.nv
+        while not self.stop_ev.is_set():
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for k, nme in enumerate(names):
-                    if r[3 + k].lower().startswith("active"):
-                        reasons.add(nme)
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons")
+                           else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for name, bit in self.REASONS:
+                    if bits & bit:
+                        self.reasons.add(name)
             except Exception:
                 pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+            self.stop_ev.wait(0.02)
+
+    def _read_cli(self):
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            try:
+                self.sm.append(float(r[0])); self.mx.append(float(r[1]))
+                for k, (name, _) in enumerate(self.REASONS):
+                    if r[3 + k].lower().startswith("active"):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+
+    def stop(self):
+        self.stop_ev.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.t:
+            self.t.join(timeout=2)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": "nvml" if getattr(self, "nv", None) else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------- CPU baseline
@@ -216,6 +244,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inflight", type=int, default=8,
                     help="verification batches in flight per GPU (one b3_ctx + host thread each; 1 = one call at a time)")
+    ap.add_argument("--pipeline-depth", type=int, default=1, choices=[1, 2],
+                    help="N > 1: a lane finishes call k after beginning call k + depth (the all-gather of a step then has depth call times to complete)")
     ap.add_argument("--h2c-msgs", type=int, default=65536, help="messages per hash_to_G2 batch of the second metric")
     ap.add_argument("--no-next-rows", action="store_true", help="skip the SURVEY 8(f) rows (decompression, aggregation, per-item verification)")
     ap.add_argument("--breakdown", action="store_true", help="print the per-stage device times to stderr")
@@ -425,6 +455,7 @@ def _bench_lanes(eng, comm, table, lanes, setup, args, world, rank, local_rank, 
     base = rank * n
     stage_acc, stage_lock = {}, threading.Lock()
 
+    by_rank = []               # ms per step of every rank, one list per timed region (N > 1)
     call_events = []           # (start, end) CUDA events around every call of a one-batch-at-a-time run (after its L2 flush)
 
     def add_stages(e):
@@ -460,7 +491,7 @@ def _bench_lanes(eng, comm, table, lanes, setup, args, world, rank, local_rank, 
         def lane_main(t):
             ln = use_lanes[t]
             e = ln.eng
-            pending = None
+            pending = []
             try:
                 with torch.cuda.stream(ln.stream):
                     h = ln.host(src) if src != "dev" else None
@@ -479,15 +510,16 @@ def _bench_lanes(eng, comm, table, lanes, setup, args, world, rank, local_rank, 
                             else:
                                 tk = e.sharded_begin(comm, ln.index, tbl, h["sigs"], h[kname], h["pk_off"], h["msgs"], h["msg_off"], h["scal"], base)
                             add_stages(e)
-                            if pending is not None:
-                                results[pending[0]] = e.sharded_finish(comm, ln.index, pending[1], want_gt=want_gt)
-                                add_stages(e)
-                            pending = (i, tk)
+                            pending.append((i, tk))
                             if L == 1 and flush_l2:                  # one call at a time: no pipelining
                                 results[i] = e.sharded_finish(comm, ln.index, tk, want_gt=want_gt)
                                 add_stages(e)
-                                pending = None
+                                pending.clear()
                                 call_events[-1][1].record()
+                            while len(pending) > args.pipeline_depth:   # finish call k only after beginning call k + depth
+                                j, tj = pending.pop(0)
+                                results[j] = e.sharded_finish(comm, ln.index, tj, want_gt=want_gt)
+                                add_stages(e)
                             continue
                         if src != "dev":                              # the reference-facing call on host pointers
                             if keys == "table":
@@ -504,8 +536,8 @@ def _bench_lanes(eng, comm, table, lanes, setup, args, world, rank, local_rank, 
                         add_stages(e)
                         if flush_l2:
                             call_events[-1][1].record()
-                    if pending is not None:
-                        results[pending[0]] = e.sharded_finish(comm, ln.index, pending[1], want_gt=want_gt)
+                    for j, tj in pending:
+                        results[j] = e.sharded_finish(comm, ln.index, tj, want_gt=want_gt)
                         add_stages(e)
             except BaseException as ex:                              # noqa: BLE001
                 errors.append(ex)
@@ -542,6 +574,9 @@ def _bench_lanes(eng, comm, table, lanes, setup, args, world, rank, local_rank, 
             ms = sum(a.elapsed_time(b) for a, b in call_events)          # the calls themselves; the 256 MiB flushes between them excluded
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            by_rank.append([round(float(x.item()) / steps, 3) for x in allt])
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         for r in res:
             assert r[0] and r[1] == -1, "verification of the valid synthetic batch must accept"
@@ -557,6 +592,12 @@ def _bench_lanes(eng, comm, table, lanes, setup, args, world, rank, local_rank, 
     # headline: S batches in flight, inputs resident in HBM, keys named by index into the resident key table
     ms_res, launches, stages_pipe, last = timed(K, W, lanes)
     clocks = sampler.stop() if rank == 0 else None
+    if os.environ.get("B3_BENCH_DIAG"):                 # diagnostic: the headline region again, now without the nvidia-smi sampler
+        timed(K, W, lanes)
+        timed(K, W, lanes)
+        if rank == 0:
+            print(json.dumps({"diag_ms_per_step_by_rank": by_rank}), flush=True)
+        return
     colls0 = comm.collectives if comm is not None else 0
     # e2e: the same from pinned HOST buffers through the host-pointer C ABI (H2D + D2H inside the timed region) ...
     ms_e2e, _, _, _ = timed(K, W, lanes, src="pinned")
@@ -728,6 +769,9 @@ def _bench_lanes(eng, comm, table, lanes, setup, args, world, rank, local_rank, 
                          "kernel_ms": dom_ms, "algorithmic_fp_muls_per_unit": FP_MULS[dom], "units_per_launch": units,
                          "frac_alone": per_stage[dom]["frac_alone"], "per_stage": per_stage,
                          "miller_loop_alone": {"ms": miller_ms, "fp_muls_per_pair": 4800,
+                                               "what": "point chains of the n message pairs + accumulation of all n + 8 pairs + closing chain, each alone (serialised "
+                                                       "pass); the point chains of the 8 signature-sum pairs (miller_lines_signature_sums, a latency-bound launch of "
+                                                       "8 lane quads on its own stream) are listed apart",
                                                "frac": 4800 * MACS_PER_FP_MUL * (n + B3_EXTRA_PAIRS) / (miller_ms * 1e-3) / peak_mac if miller_ms else None},
                          "stage_ms": stages, "stage_ms_serialised": stages_serial,
                          "note": "kernel spans (stage_ms, frac) come from the one-batch-in-flight timed region (L2 flushed before every step): "
@@ -792,6 +836,7 @@ def _bench_lanes(eng, comm, table, lanes, setup, args, world, rank, local_rank, 
            "next_rows": next_rows,
            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
            "accept": bool(last[0]),
+           "ms_per_step_by_rank": by_rank if world > 1 else None,
            "checks": "valid batch: same GT on every rank and for both key forms; tampered message on the last rank: reject on every rank with one GT; non-subgroup signature on the last rank: global first_bad on every rank"}
     if args.breakdown:
         print(json.dumps({"overlapped": stages, "serialised": stages_serial, "pipelined": stages_pipe}, indent=1), file=sys.stderr)

@@ -26,11 +26,12 @@ static const size_t kDstG2Len = 43;
 // sets from which the key aggregation uses 4 lanes per set instead of 8 (less shuffle-tree overhead, twice the latency)
 static const size_t kAggG4Min = getenv("B3_AGG_G4_MIN") ? (size_t)atol(getenv("B3_AGG_G4_MIN")) : 4096;
 #define B3_MSM_MIN_SETS 512     // below this, S = sum [c_j] sig_j uses n separate ladders + a tree
-#define B3_N_STAGES 11
+#define B3_N_STAGES 12
 // stage ids (b3_ctx_stage_ms / b3_stage_name)
-enum { ST_SIG_CHECK = 0, ST_AGGREGATE, ST_G1_MUL, ST_HASH_TO_G2, ST_G2_MUL_SUM, ST_MILLER, ST_FP12_PRODUCT, ST_FINAL_EXP, ST_COPY, ST_MILLER_LINES, ST_END };
+enum { ST_SIG_CHECK = 0, ST_AGGREGATE, ST_G1_MUL, ST_HASH_TO_G2, ST_G2_MUL_SUM, ST_MILLER, ST_FP12_PRODUCT, ST_FINAL_EXP, ST_COPY, ST_MILLER_LINES, ST_MILLER_LINES_SUMS, ST_END };
 static const char* kStageNames[B3_N_STAGES] = {"g2_parse_subgroup_check", "g1_aggregate", "g1_scalar_mul_affine", "hash_to_g2_affine",
-                                               "g2_scalar_mul_sum", "miller_accumulate", "miller_chain", "final_exp", "parse_copies", "miller_lines", "end"};
+                                               "g2_scalar_mul_sum", "miller_accumulate", "miller_chain", "final_exp", "parse_copies", "miller_lines",
+                                               "miller_lines_signature_sums", "end"};
 
 struct dev_buf {
     void* p = nullptr;
@@ -52,6 +53,7 @@ struct b3_ctx {
     // independent stages of verify_multiple run concurrently on aux streams (fork/join by events) unless serial != 0
     cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_fork2 = nullptr, ev_fork3 = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_sync = nullptr;  // blocking-sync event: the host thread of a call SLEEPS while it waits (see sync())
     bool sig_pending = false;       // the subgroup checks of the call run on aux[0] beside the closing chain: join before reading first_bad
     int serial = 0;
     int latency_mode = 0;           // chain kernels: 0 = replicated lanes (quad.cuh) when this is the only call in flight on the device, 1 = always, 2 = never
@@ -134,6 +136,7 @@ extern "C" int b3_ctx_create(int device, b3_ctx** out) {
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork3, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
     for (int i = 0; i < B3_N_STAGES; i++) ctx->stage_ms[i] = 0.f;
     ok = ok && cudaMalloc((void**)&ctx->d_dst, 256) == cudaSuccess;
     ok = ok && cudaMemcpy(ctx->d_dst, kDstG2, kDstG2Len, cudaMemcpyHostToDevice) == cudaSuccess;
@@ -168,6 +171,7 @@ extern "C" void b3_ctx_destroy(b3_ctx* ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_fork2) cudaEventDestroy(ctx->ev_fork2);
     if (ctx->ev_fork3) cudaEventDestroy(ctx->ev_fork3);
+    if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     cudaGetLastError();
     delete ctx;
@@ -227,8 +231,18 @@ static int d2h(b3_ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return B3_OK;
 }
+// Wait for the context's stream.  The waiting host thread BLOCKS on a blocking-sync event instead of spinning in
+// cudaStreamSynchronize: the drop-in model is one host thread per call in flight (eight per GPU in bench.py), and on an
+// 8-GPU box 64 spinning threads on 32 cores starve the threads that launch kernels (measured: 8.1 M sets/s at N = 8
+// spinning).  B3_SPIN_SYNC=1 restores the spinning wait.
 static int sync(b3_ctx* ctx) {
-    CK(cudaStreamSynchronize(ctx->stream));
+    static const bool spin = getenv("B3_SPIN_SYNC") && atoi(getenv("B3_SPIN_SYNC")) != 0;
+    if (spin) {
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+        CK(cudaEventRecord(ctx->ev_sync, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev_sync));
+    }
     CK(cudaGetLastError());
     return B3_OK;
 }
@@ -275,7 +289,7 @@ static int g2_sum(b3_ctx* ctx, g2_jac* a, g2_jac* b, size_t n, g2_jac** res, cud
 // -> lines in HBM (68 x n_pairs x 288 B).  May be issued on any stream as soon as those q's exist.
 static int miller_lines(b3_ctx* ctx, cudaStream_t strm, const g2_jac* q, size_t n_pairs, size_t first, size_t count) {
     if (count == 0) return B3_OK;
-    int sp = span_begin(ctx, ST_MILLER_LINES, strm);
+    int sp = span_begin(ctx, count <= 64 && first > 0 ? ST_MILLER_LINES_SUMS : ST_MILLER_LINES, strm);   // the few pairs of the signature MSM are timed apart
     if (ctx->wide_now || count <= 64)          // few pairs (the window sums of the signature MSM): always latency-bound
         LAUNCH_ON(strm, k_miller_lines_q, nblk(4 * count), B3_TPB, q, n_pairs, first, count, (fp2*)ctx->lines.p, (uint32_t*)ctx->qinf.p);
     else
