@@ -370,6 +370,16 @@ __device__ __forceinline__ void fp_dot3_rs(fp& r, const fp& a0, const fp& a1, co
 }
 #endif
 
+#if !defined(B3_HOSTSIM)
+// out-of-line form (operands and result in registers): ONE copy of the 588-product body instead of one per call site -- the
+// accumulation kernel calls it three times per line and its fully unrolled loop body no longer fit the instruction cache
+__device__ __noinline__ fp fp_dot3_rs_v(fp a0, fp a1, fp a2, const fp* b0, const fp* b1, const fp* b2) {
+    fp r;
+    fp_dot3_rs(r, a0, a1, a2, b0, b1, b2);
+    return r;
+}
+#endif
+
 // Montgomery SQUARING  r = a^2 / 2^384 mod p  (a < p), row-wise with the same interleaved reduction as fp_mul_inl, but using
 //   a^2 = sum_i a_i 2^(32 i) * ( a_i 2^(32 i) + 2 sum_{j>i} a_j 2^(32 j) ):
 // row i adds a_i times the limbs j >= i of that bracket only -- a_i itself at j = i, a_(i+1) << 1 at j = i + 1 and the limbs

@@ -996,9 +996,9 @@ __global__ void __launch_bounds__(B3_TPB, 3) k_miller_accum(const fp2* __restric
                 // r = sum_t A_t B_t over the three (coefficient, line operand) pairs, Karatsuba with three reductions:
                 //   R2 = sum (A.c0 + A.c1)(B.c0 + B.c1), R0 = sum A.c0 B.c0, R1 = sum A.c1 B.c1;  re = R0 - R1, im = R2 - R0 - R1
                 fp R0, R1, R2;
-                fp_dot3_rs(R2, as0, as1, as2, o + 10, o + 10 + x3, o + 10 + x5);
-                fp_dot3_rs(R0, a[0], a[2], a[4], o, o + x3, o + x5);
-                fp_dot3_rs(R1, a[1], a[3], a[5], o + 5, o + 5 + x3, o + 5 + x5);
+                R2 = fp_dot3_rs_v(as0, as1, as2, o + 10, o + 10 + x3, o + 10 + x5);
+                R0 = fp_dot3_rs_v(a[0], a[2], a[4], o, o + x3, o + x5);
+                R1 = fp_dot3_rs_v(a[1], a[3], a[5], o + 5, o + 5 + x3, o + 5 + x5);
                 fp_sub(a[0], R0, R1);
                 fp_sub(R2, R2, R0);
                 fp_sub(a[1], R2, R1);
