@@ -541,6 +541,15 @@ def test_verify_multiple_latency_modes_vs_c_oracle(eng, mode):
         bad = sig.copy(); bad[377] = np.frombuffer(g2w(O.map_to_curve_g2((5, 7))), dtype=np.uint8)
         ok, fb = eng.verify_multiple(bad.reshape(-1), pk.reshape(-1), offs, b"".join(msgs), moff, scalars)
         assert not ok and fb == 377
+        # the partial form (sharded path): its subgroup checks start with the call and use this mode's kernel
+        import torch
+        part = torch.zeros(592, dtype=torch.uint8, device="cuda:0")
+        torch.cuda.synchronize()
+        eng.verify_multiple_partial(sw.reshape(-1), pk.reshape(-1), offs, b"".join(msgs), moff, scalars, 0, part.data_ptr())
+        assert eng.combine_partials_dev(part.data_ptr(), 1, want_gt=True) == (False, -1, gt_c)
+        eng.verify_multiple_partial(bad.reshape(-1), pk.reshape(-1), offs, b"".join(msgs), moff, scalars, 1000, part.data_ptr())
+        ok, fb = eng.combine_partials_dev(part.data_ptr(), 1)
+        assert not ok and fb == 1377                                     # index_base + 377
     finally:
         eng.set_latency_mode(0)
 
