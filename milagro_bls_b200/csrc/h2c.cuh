@@ -83,8 +83,12 @@ B3_FN void sha256_put_word(sha256_ctx& c, uint32_t be_word) {
 B3_FN void sha256_update(sha256_ctx& c, const uint8_t* p, uint32_t n) {
     uint32_t i = 0;
 #if !defined(B3_HOSTSIM)
-    if ((reinterpret_cast<uintptr_t>(p) & 3u) == 0 && (c.fill & 3u) == 0)        // aligned input: 32-bit loads
-        for (; i + 4 <= n; i += 4) sha256_put_word(c, b3_bswap(__ldg(reinterpret_cast<const uint32_t*>(p + i))));
+    if ((reinterpret_cast<uintptr_t>(p) & 3u) == 0 && (c.fill & 3u) == 0) {      // aligned input: 32-bit loads
+        if (__isGlobal(p))
+            for (; i + 4 <= n; i += 4) sha256_put_word(c, b3_bswap(__ldg(reinterpret_cast<const uint32_t*>(p + i))));
+        else                                                                      // message staged in shared memory (k_hash_to_g2)
+            for (; i + 4 <= n; i += 4) sha256_put_word(c, b3_bswap(*reinterpret_cast<const uint32_t*>(p + i)));
+    }
 #endif
     for (; i < n; i++) sha256_put(c, p[i]);
 }

@@ -747,16 +747,36 @@ __global__ void __launch_bounds__(B3_TPB) k_g2_aff_to_wire(const g2_aff* in, siz
 // Two threads per message.  Phase 1: each lane maps ONE of the two field elements to the curve (SSWU + 3-isogeny,
 // single-thread Fp2 arithmetic: the square roots are chains of Fp operations).  Phase 2: the two points are
 // redistributed into lane-pair form and the pair adds them and clears the cofactor together.
+// The messages of a CTA (64 of them, contiguous in the blob) are STAGED: the CTA copies the byte range of its messages into
+// shared memory with coalesced 16-byte loads (whole 16-byte words of the range; its ragged tail byte by byte) and every lane
+// hashes from there.  Ranges that do not fit the stage (long messages) are read from global memory directly.
+#define B3_H2C_STAGE_BYTES 4096
 __global__ void __launch_bounds__(B3_TPB, B3_H2C_CTAS) k_hash_to_g2(const uint8_t* __restrict__ msgs, const uint32_t* __restrict__ off, size_t n,
                                                        const uint8_t* __restrict__ dst, uint32_t dst_len, g2_jac* out) {
+    __shared__ uint4 stage[B3_H2C_STAGE_BYTES / 16];
     size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    const size_t m0 = ((size_t)blockIdx.x * blockDim.x) >> 1;                     // first message of this CTA (m0 < n for every CTA)
+    const size_t m1 = m0 + (blockDim.x >> 1) < n ? m0 + (blockDim.x >> 1) : n;
+    const uint32_t lo = off[m0], hi = off[m1];
+    const uint32_t lo16 = lo & ~15u;
+    const bool staged = hi - lo16 <= B3_H2C_STAGE_BYTES && (reinterpret_cast<uintptr_t>(msgs) & 15u) == 0;
+    if (staged) {
+        const uint32_t len = hi - lo16;
+        for (uint32_t w = threadIdx.x; 16 * w < len; w += blockDim.x) {
+            if (16 * w + 16 <= len) stage[w] = __ldg(reinterpret_cast<const uint4*>(msgs + lo16) + w);
+            else
+                for (uint32_t t = 16 * w; t < len; t++) reinterpret_cast<uint8_t*>(stage)[t] = msgs[lo16 + t];
+        }
+    }
+    __syncthreads();
     if (i >= n) return;
     const bool odd = pair_odd();
     uint32_t b = off[i], e = off[i + 1];
+    const uint8_t* msg = staged ? reinterpret_cast<const uint8_t*>(stage) + (b - lo16) : msgs + b;
     g2_jac q;
     {
         fp2 u0, u1, u;
-        hash_to_field_fp2_x2(u0, u1, msgs + b, e - b, dst, dst_len);
+        hash_to_field_fp2_x2(u0, u1, msg, e - b, dst, dst_len);
         fp2_select(u, odd, u1, u0);
         map_to_curve_g2(q, u);
     }
