@@ -7,7 +7,10 @@ Contract (see the task statement):  python bench.py --gpus N --steps K --warmup 
     is BASELINE.json configs[4] (2^16 sets, NCCL combine of the 592-byte partial Miller products).
   * one call = one full verification of a C4 batch: G2 subgroup checks, G1 key aggregation, [c]apk, hash_to_G2,
     [c]sig sum, n+8 Miller loops, Fp12 product, (all-gather,) one final exponentiation, accept bit.
-  * a step = one such call on EACH of --inflight (default 8) contexts per GPU, running concurrently: one b3_ctx + one
+  * a step = one such call on EACH of --inflight (default 8) contexts per GPU, running concurrently.  Four are enough to
+    saturate one B200 (profiles/r2_calls_in_flight.txt: 1.13 M sets/s with one call in flight, 1.40 M with two, 1.52 M with
+    three, 1.60 M with four, 1.60-1.62 M with 6..16); eight give the sharded run the slack that hides the other ranks' jitter
+    at the all-gather (N = 8: 12.08 M sets/s with eight, 11.57 M with four).  One b3_ctx + one
     host thread per call, the reference's own threading model (re-entrant types, callers parallelise externally).  A
     single 8192-set call is a chain of latency-bound kernels (~7 ms end to end) that cannot fill 148 SMs by itself;
     K steps = K x inflight full verifications of 8192 sets each.
@@ -592,9 +595,12 @@ def _bench_lanes(eng, comm, table, lanes, setup, args, world, rank, local_rank, 
     # headline: S batches in flight, inputs resident in HBM, keys named by index into the resident key table
     ms_res, launches, stages_pipe, last = timed(K, W, lanes)
     clocks = sampler.stop() if rank == 0 else None
-    if os.environ.get("B3_BENCH_DIAG"):                 # diagnostic: the headline region again, now without the nvidia-smi sampler
-        timed(K, W, lanes)
-        timed(K, W, lanes)
+    if os.environ.get("B3_BENCH_DIAG"):                 # diagnostic: the headline region again, now without the clock sampler
+        m2 = timed(K, W, lanes)[0]
+        m3 = timed(K, W, lanes)[0]
+        if rank == 0 and os.environ.get("B3_BENCH_PRINT_HEADLINE"):
+            print("headline_region ms_per_step", [round(x / K, 3) for x in (ms_res, m2, m3)], "sets/s",
+                  [round(n * world * S * K / (x * 1e-3)) for x in (ms_res, m2, m3)], flush=True)
         if rank == 0:
             print(json.dumps({"diag_ms_per_step_by_rank": by_rank}), flush=True)
         return
