@@ -5,8 +5,11 @@ rank r verifies its shard with global set indices (so `first_bad` means the same
 592-byte partial (Miller-loop product + first failing index).  ONE all-gather of the partials is the only collective
 on the path; every rank then multiplies the partials and runs the single final exponentiation.
 
-The functions take the process group explicitly and only move bytes, so the same code runs over NCCL (GPU tensors,
-bench.py) and over gloo (CPU tensors, tests/test_sharding.py).
+The product's collective lives INSIDE the C library (b3_comm_create / b3_verify_multiple_sharded: ncclAllGather issued by the
+library, include/milagro_bls_b200.h; bench.py and tests/test_gpu_multirank.py use that).  This module holds the host-side
+shard arithmetic and the same exchange written over torch.distributed for hosts that run their own collective
+(b3_verify_multiple_partial* + b3_combine_partials_dev): it only moves bytes, so it runs over NCCL (GPU tensors) and over
+gloo (CPU tensors, tests/test_sharding.py).
 """
 import torch
 import torch.distributed as dist
