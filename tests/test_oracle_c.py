@@ -101,3 +101,41 @@ def test_cpu_baseline_runs():
     from oracle import cpu_baseline
     r = cpu_baseline.run(2, 4, seed=1, threads=2)
     assert r["sets"] == 2 and r["kind"] == "port" and r["seconds"] > 0
+
+
+def test_c_field_layer_variants_agree(tmp_path):
+    """The macro-gated field-layer variants of the C oracle (-DORACLE_SQR_DEDICATED: dedicated squaring; -DORACLE_FP2_LAZY:
+    lazily reduced Fp2 product; the Makefile builds the combination measured fastest) compute the same bytes: hash_to_G2 of
+    the golden messages and a rejecting 3-set verify_multiple GT, for all four combinations."""
+    import ctypes
+    import subprocess
+    src = os.path.join(os.path.dirname(C.HERE), "oracle", "bls_oracle_c.c")
+    vec = json.load(open(os.path.join(G, "h2c_g2_ro.json")))
+    sks = [11, 22, 33]
+    msgs = [b"m0", b"m1-longer", b""]
+    sig = b"".join(g2w(O.sign(s, m)) for s, m in zip(sks, msgs))
+    pk = b"".join(g1w(O.sk_to_pk(s)) for s in sks)
+    blob = b"".join(msgs[::-1])                                     # messages in the wrong order: GT != 1
+    moff = np.array([0, 0, 9, 11], dtype=np.uint32)
+    scal = np.array([3, 5, 7], dtype=np.uint64)
+    outs = []
+    for k, defs in enumerate(([], ["-DORACLE_SQR_DEDICATED"], ["-DORACLE_FP2_LAZY"], ["-DORACLE_SQR_DEDICATED", "-DORACLE_FP2_LAZY"])):
+        so = str(tmp_path / f"liboc_{k}.so")
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-Wno-unused-function", "-shared", "-o", so, src] + defs)
+        L = ctypes.CDLL(so)
+        h = []
+        for v in vec["vectors"]:
+            out = np.zeros(192, dtype=np.uint8)
+            m, d = np.frombuffer(v["msg"].encode() or b"\0", dtype=np.uint8), np.frombuffer(vec["dst"].encode(), dtype=np.uint8)
+            L.oc_hash_to_g2(ctypes.c_void_p(m.ctypes.data), ctypes.c_size_t(len(v["msg"])), ctypes.c_void_p(d.ctypes.data), ctypes.c_size_t(len(d)),
+                            ctypes.c_void_p(out.ctypes.data))
+            P = ((int(v["P"]["x"][0], 16), int(v["P"]["x"][1], 16)), (int(v["P"]["y"][0], 16), int(v["P"]["y"][1], 16)))
+            assert out.tobytes() == g2w(P)
+            h.append(out.tobytes())
+        gt = np.zeros(576, dtype=np.uint8)
+        a = [np.frombuffer(x, dtype=np.uint8) for x in (sig, pk, blob)]
+        rc = L.oc_verify_multiple(ctypes.c_void_p(a[0].ctypes.data), ctypes.c_void_p(a[1].ctypes.data), None, ctypes.c_void_p(a[2].ctypes.data),
+                                  ctypes.c_void_p(moff.ctypes.data), ctypes.c_void_p(scal.ctypes.data), ctypes.c_size_t(3), ctypes.c_void_p(gt.ctypes.data))
+        outs.append((h, rc, gt.tobytes()))
+    assert all(o == outs[0] for o in outs[1:])
+    assert outs[0][2] != O.f12_to_bytes(O.F12_ONE)
